@@ -1,0 +1,145 @@
+/*
+ * b200sort.h -- C-ABI of libb200sort.so, the B200 (sm_100a) sort library that sits behind the
+ * lab's operator boundary.
+ *
+ * Plain C: pointers, sizes and ints only.  Every function returns a B200SORT_* status (0 = ok)
+ * unless stated otherwise, never exits the process, and is stream-ordered: it enqueues work on
+ * `stream` (a cudaStream_t passed as void*, NULL = the legacy default stream) and returns without
+ * synchronising unless its comment says it blocks.
+ *
+ * Reference interface each entry point replaces ("SRM/" = "/root/reference/Sord Radix y Merge/"):
+ *
+ *   b200sort_order_array_host   SRM/include/lab.h:9  + SRM/lab.cu:303-402  order_array(int*,int)
+ *   b200sort_order_with_trust_host  SRM/include/lab.h:10 + SRM/lab.cu:404-406 order_with_trust(int*,int)
+ *   b200sort_radix_i32          SRM/lab.cu:47-87   radix_sort_kernel (the radix stage), rebuilt as a
+ *                               full onesweep LSD sort
+ *   b200sort_radix_histogram_i32 / b200sort_radix_pass_i32
+ *                               SRM/lab.cu:11-41 exlusiveScan + :63-76 split, i.e. the count/scan/
+ *                               scatter the lab does per bit, here per 8-bit digit
+ *   b200sort_merge_i32          SRM/lab.cu:192-197 orderedJoin + :209-300 separators_kernel /
+ *                               merge_segments_kernel (the merge stages), rebuilt as block sort +
+ *                               merge-path merges
+ *   b200sort_block_sort_i32     SRM/lab.cu:328-344 (stage 1 + stage 2: sorted runs inside a block)
+ *   b200sort_merge_partition_i32 SRM/lab.cu:209-270 separators_kernel
+ *   b200sort_merge_pass_i32     SRM/lab.cu:272-300 merge_segments_kernel
+ *   b200sort_lab_i32            SRM/lab.cu:303-402 the assignment's staged pipeline kept as a third
+ *                               algorithm (warp-tile split -> rank merge -> merge path)
+ *   b200sort_dist_*             no reference counterpart (north_star (c)): one-box multi-GPU sort
+ *
+ * The C++ symbols order_array(int*,int) / order_with_trust(int*,int) that SRM/main.cpp and
+ * SRM/performanceTest.cpp link against are exported by the same library (csrc/lab_shim.cu) with
+ * the reference's abort-on-error convention (SRM/include/utils.h:18-26); see include/lab.h.
+ */
+#ifndef B200SORT_H
+#define B200SORT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status ------------------------------------------------------------------------------------ */
+#define B200SORT_OK                 0
+#define B200SORT_ERR_INVALID        1   /* bad argument (NULL pointer, unknown algorithm, n too large) */
+#define B200SORT_ERR_WORKSPACE      2   /* workspace NULL / too small / misaligned */
+#define B200SORT_ERR_CUDA           3   /* a CUDA runtime call failed; see b200sort_last_cuda_error */
+#define B200SORT_ERR_NO_DEVICE      4   /* no usable sm_100 device: there is NO CPU fallback */
+#define B200SORT_ERR_ALLOC          5   /* host-path allocation failed */
+
+/* ---- algorithms -------------------------------------------------------------------------------- */
+#define B200SORT_ALGO_RADIX         0   /* onesweep LSD radix, 8-bit digits, 4 passes */
+#define B200SORT_ALGO_MERGE         1   /* register bitonic block sort + merge-path merges */
+#define B200SORT_ALGO_LAB           2   /* the assignment's staged pipeline (radix tiles -> merges) */
+
+/* Largest n any entry point accepts (tile-status words carry 30-bit counts). */
+#define B200SORT_MAX_N              ((size_t)1 << 30)
+
+const char *b200sort_version(void);
+const char *b200sort_status_string(int status);
+/* cudaError_t (as int) of the most recent failing CUDA call on this host thread, 0 if none. */
+int         b200sort_last_cuda_error(void);
+const char *b200sort_last_cuda_error_string(void);
+/* B200SORT_OK iff the current device exists and is compute capability 10.x. */
+int         b200sort_device_check(void);
+
+/* ---- device-array sorts (the layer measured against the HBM roofline) --------------------------
+ * d_keys  n keys, sorted in place (ascending, signed).
+ * d_tmp   n keys of scratch (ping-pong buffer); contents undefined on return.
+ * d_ws    workspace of at least b200sort_workspace_bytes(n, algo) bytes, 256-byte aligned;
+ *         need not be initialised; may be reused by the next call on the same stream.
+ * Any n in [0, B200SORT_MAX_N]; the lab's n (power of two, multiple of 32) is the tested case,
+ * ragged n is handled. */
+size_t b200sort_workspace_bytes(size_t n, int algo);
+int    b200sort_radix_i32(int32_t *d_keys, int32_t *d_tmp, size_t n,
+                          void *d_ws, size_t ws_bytes, void *stream);
+int    b200sort_merge_i32(int32_t *d_keys, int32_t *d_tmp, size_t n,
+                          void *d_ws, size_t ws_bytes, void *stream);
+int    b200sort_sort_i32(int algo, int32_t *d_keys, int32_t *d_tmp, size_t n,
+                         void *d_ws, size_t ws_bytes, void *stream);
+/* Out-of-place form: d_out = sorted d_in; d_in is only read (it may also equal d_out).  No extra
+ * traffic compared with the in-place form: the first pass simply reads d_in. */
+int    b200sort_sort_copy_i32(int algo, const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n,
+                              void *d_ws, size_t ws_bytes, void *stream);
+/* Same as b200sort_sort_copy_i32 with CUDA events around the kernels; BLOCKS until done.
+ * radix: ms[0] histogram, ms[1..4] the four passes, ms[5] final copy (6 floats).
+ * merge: ms[0] block sort, ms[1] all merge passes together, ms[2] number of merge passes. */
+int    b200sort_sort_timed_i32(int algo, const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n,
+                               void *d_ws, size_t ws_bytes, void *stream, float *ms);
+
+/* ---- stages, exposed for unit tests and per-kernel timing -------------------------------------- */
+
+/* d_hist[p*256+d] (uint32) = number of keys whose digit p of (key ^ 0x80000000) equals d.
+ * One read of the keys with 128-bit loads.  d_hist is overwritten. */
+int b200sort_radix_histogram_i32(const int32_t *d_keys, size_t n, uint32_t *d_hist, void *stream);
+/* One stable onesweep pass by digit `pass` (0..3): d_out = d_in partitioned by that digit.
+ * d_in and d_out must not overlap.  Uses the radix workspace. */
+int b200sort_radix_pass_i32(const int32_t *d_in, int32_t *d_out, size_t n, int pass,
+                            void *d_ws, size_t ws_bytes, void *stream);
+/* Keys per tile of the block sort (every aligned run of this many keys comes out sorted). */
+size_t b200sort_block_sort_tile(void);
+int b200sort_block_sort_i32(const int32_t *d_in, int32_t *d_out, size_t n, void *stream);
+/* Keys per output tile of a merge pass. */
+size_t b200sort_merge_tile(void);
+/* Merge-path split points for one pass over sorted runs of `run` keys (run a multiple of
+ * b200sort_merge_tile()): d_splits[t] = number of keys taken from the pair's first run before
+ * output tile t begins.  d_splits holds ceil(n / merge_tile) + 1 uint32. */
+int b200sort_merge_partition_i32(const int32_t *d_in, size_t n, size_t run,
+                                 uint32_t *d_splits, void *stream);
+/* The pass itself: merges run pairs of d_in into d_out using d_splits. */
+int b200sort_merge_pass_i32(const int32_t *d_in, int32_t *d_out, size_t n, size_t run,
+                            const uint32_t *d_splits, void *stream);
+
+/* ---- tuning / introspection --------------------------------------------------------------------- */
+/* Selects one of the compiled onesweep tile shapes (0 = default); returns B200SORT_ERR_INVALID
+ * if out of range.  Process-wide; for sweeps only. */
+int         b200sort_radix_set_variant(int variant);
+int         b200sort_radix_num_variants(void);
+const char *b200sort_radix_variant_name(int variant);
+size_t      b200sort_radix_tile(void);            /* keys per onesweep tile of the current variant */
+/* Pass skipping: when a digit histogram shows one bin holding every key the pass is the
+ * identity and is skipped on the device (no host sync).  1 = on (default), 0 = off. */
+int         b200sort_radix_set_skip(int enabled);
+/* Kernels this library has launched on this host thread since the last reset (all entry
+ * points count their own launches; memsets and copies are not kernels and are not counted). */
+unsigned long long b200sort_launch_count(void);
+void               b200sort_launch_count_reset(void);
+
+/* ---- host-array operator (the reference's real contract: SRM/include/lab.h:9-10) ---------------
+ * Sorts h_keys[0..n) in place and BLOCKS until the result is in h_keys.  The library keeps a
+ * per-process device arena (keys, scratch, workspace, pinned staging) that grows on demand and is
+ * reused across calls; b200sort_host_release frees it.  h_keys may be pageable or pinned. */
+int  b200sort_order_array_host(int32_t *h_keys, size_t n, int algo);
+/* What the exported C++ order_with_trust calls: the same host-array contract served by the
+ * merge sort (the drivers' second column).  There is no host/CPU sort in this library. */
+int  b200sort_order_with_trust_host(int32_t *h_keys, size_t n);
+void b200sort_host_release(void);
+/* Pinned host memory helpers for callers that want the fast H2D/D2H path. */
+int  b200sort_host_alloc_pinned(void **h_ptr, size_t bytes);
+int  b200sort_host_free_pinned(void *h_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SORT_H */

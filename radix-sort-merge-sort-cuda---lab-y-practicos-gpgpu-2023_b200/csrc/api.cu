@@ -1,0 +1,309 @@
+// api.cu -- the extern "C" surface of libb200sort.so (include/b200sort.h) and the host-array
+// operator that stands where the lab's order_array stood (SRM/lab.cu:303-402).
+#include "common.cuh"
+#include "merge.cuh"
+#include "radix.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace b200sort {
+
+thread_local cudaError_t g_last_cuda_error = cudaSuccess;
+thread_local unsigned long long g_launch_count = 0;
+
+// declared in radix.cu
+int radix_num_variants();
+const char *radix_variant_name(int v);
+int radix_set_variant(int v);
+void radix_set_skip(int enabled);
+
+namespace {
+
+int device_check() {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { g_last_cuda_error = e; cudaGetLastError(); return B200SORT_ERR_NO_DEVICE; }
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) { g_last_cuda_error = e; cudaGetLastError(); return B200SORT_ERR_NO_DEVICE; }
+    return major == 10 ? B200SORT_OK : B200SORT_ERR_NO_DEVICE;
+}
+
+int check_sort_args(const void *keys, const void *tmp, size_t n) {
+    if (n > B200SORT_MAX_N) return B200SORT_ERR_INVALID;
+    if (n > 1 && (keys == nullptr || tmp == nullptr)) return B200SORT_ERR_INVALID;
+    return B200SORT_OK;
+}
+
+// ---- the per-process arena behind the host-array operator ---------------------------------------
+constexpr size_t kStageBytes = 16u << 20;      // pinned staging chunk for pageable callers
+constexpr size_t kDirectBytes = 1u << 20;      // below this a plain memcpy is as good as staging
+
+struct HostArena {
+    std::mutex mu;
+    int device = -1;
+    int32_t *d_keys = nullptr, *d_tmp = nullptr;
+    size_t cap_keys = 0;
+    void *d_ws = nullptr;
+    size_t cap_ws = 0;
+    void *h_stage[2] = {nullptr, nullptr};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+
+    void release() {
+        if (d_keys) cudaFree(d_keys);
+        if (d_tmp) cudaFree(d_tmp);
+        if (d_ws) cudaFree(d_ws);
+        for (int i = 0; i < 2; ++i) {
+            if (h_stage[i]) cudaFreeHost(h_stage[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+            h_stage[i] = nullptr; ev[i] = nullptr;
+        }
+        if (stream) cudaStreamDestroy(stream);
+        d_keys = d_tmp = nullptr; d_ws = nullptr; stream = nullptr;
+        cap_keys = cap_ws = 0; device = -1;
+    }
+
+    int ensure(size_t n, size_t ws_bytes) {
+        int dev = 0;
+        B200_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev != device) { release(); device = dev; }
+        if (stream == nullptr) {
+            B200_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) B200_CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        if (n > cap_keys) {
+            if (d_keys) cudaFree(d_keys);
+            if (d_tmp) cudaFree(d_tmp);
+            d_keys = d_tmp = nullptr; cap_keys = 0;
+            size_t cap = 1024;
+            while (cap < n) cap *= 2;
+            B200_CUDA_TRY(cudaMalloc(&d_keys, cap * sizeof(int32_t)));
+            B200_CUDA_TRY(cudaMalloc(&d_tmp, cap * sizeof(int32_t)));
+            cap_keys = cap;
+        }
+        if (ws_bytes > cap_ws) {
+            if (d_ws) cudaFree(d_ws);
+            d_ws = nullptr; cap_ws = 0;
+            B200_CUDA_TRY(cudaMalloc(&d_ws, ws_bytes));
+            cap_ws = ws_bytes;
+        }
+        return B200SORT_OK;
+    }
+
+    int ensure_stage() {
+        for (int i = 0; i < 2; ++i)
+            if (h_stage[i] == nullptr) B200_CUDA_TRY(cudaMallocHost(&h_stage[i], kStageBytes));
+        return B200SORT_OK;
+    }
+};
+
+HostArena &arena() {
+    static HostArena a;
+    return a;
+}
+
+bool is_device_accessible_host(const void *p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+// Pageable -> device through two pinned chunks: the CPU fills one while the DMA drains the other.
+int h2d(HostArena &a, int32_t *d, const int32_t *h, size_t bytes) {
+    if (bytes <= kDirectBytes || is_device_accessible_host(h)) {
+        B200_CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, a.stream));
+        return B200SORT_OK;
+    }
+    B200_TRY(a.ensure_stage());
+    const char *src = reinterpret_cast<const char *>(h);
+    char *dst = reinterpret_cast<char *>(d);
+    int slot = 0;
+    for (size_t off = 0; off < bytes; off += kStageBytes, slot ^= 1) {
+        const size_t len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+        B200_CUDA_TRY(cudaEventSynchronize(a.ev[slot]));       // previous DMA out of this chunk done
+        std::memcpy(a.h_stage[slot], src + off, len);
+        B200_CUDA_TRY(cudaMemcpyAsync(dst + off, a.h_stage[slot], len, cudaMemcpyHostToDevice, a.stream));
+        B200_CUDA_TRY(cudaEventRecord(a.ev[slot], a.stream));
+    }
+    return B200SORT_OK;
+}
+
+int d2h(HostArena &a, int32_t *h, const int32_t *d, size_t bytes) {
+    if (bytes <= kDirectBytes || is_device_accessible_host(h)) {
+        B200_CUDA_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, a.stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(a.stream));
+        return B200SORT_OK;
+    }
+    B200_TRY(a.ensure_stage());
+    char *dst = reinterpret_cast<char *>(h);
+    const char *src = reinterpret_cast<const char *>(d);
+    const size_t chunks = div_up(bytes, kStageBytes);
+    for (size_t c = 0; c <= chunks; ++c) {
+        if (c < chunks) {
+            const size_t off = c * kStageBytes;
+            const size_t len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+            B200_CUDA_TRY(cudaMemcpyAsync(a.h_stage[c & 1], src + off, len, cudaMemcpyDeviceToHost, a.stream));
+            B200_CUDA_TRY(cudaEventRecord(a.ev[c & 1], a.stream));
+        }
+        if (c > 0) {
+            const size_t off = (c - 1) * kStageBytes;
+            const size_t len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+            B200_CUDA_TRY(cudaEventSynchronize(a.ev[(c - 1) & 1]));
+            std::memcpy(dst + off, a.h_stage[(c - 1) & 1], len);
+        }
+    }
+    return B200SORT_OK;
+}
+
+int sort_dispatch(int algo, const int32_t *in, int32_t *out, int32_t *t, size_t n, void *ws, size_t wsb,
+                  cudaStream_t s, float *ms = nullptr) {
+    switch (algo) {
+        case B200SORT_ALGO_RADIX: return ms ? radix_sort_timed(in, out, t, n, ws, wsb, s, ms)
+                                            : radix_sort(in, out, t, n, ws, wsb, s);
+        case B200SORT_ALGO_MERGE: return merge_sort(in, out, t, n, ws, wsb, s, ms);
+        default: return B200SORT_ERR_INVALID;
+    }
+}
+
+size_t workspace_bytes(size_t n, int algo) {
+    switch (algo) {
+        case B200SORT_ALGO_RADIX: return radix_workspace_bytes(n);
+        case B200SORT_ALGO_MERGE: return merge_workspace_bytes(n);
+        default: return 0;
+    }
+}
+
+int order_host(int32_t *h_keys, size_t n, int algo) {
+    if (n > B200SORT_MAX_N) return B200SORT_ERR_INVALID;
+    if (algo != B200SORT_ALGO_RADIX && algo != B200SORT_ALGO_MERGE) return B200SORT_ERR_INVALID;
+    if (n <= 1) return B200SORT_OK;
+    if (h_keys == nullptr) return B200SORT_ERR_INVALID;
+    B200_TRY(device_check());
+    HostArena &a = arena();
+    std::lock_guard<std::mutex> lock(a.mu);
+    const size_t wsb = workspace_bytes(n, algo);
+    B200_TRY(a.ensure(n, wsb));
+    const size_t bytes = n * sizeof(int32_t);
+    B200_TRY(h2d(a, a.d_keys, h_keys, bytes));
+    B200_TRY(sort_dispatch(algo, a.d_keys, a.d_keys, a.d_tmp, n, a.d_ws, a.cap_ws, a.stream));
+    B200_TRY(d2h(a, h_keys, a.d_keys, bytes));
+    B200_CUDA_TRY(cudaStreamSynchronize(a.stream));
+    return B200SORT_OK;
+}
+
+}  // namespace
+}  // namespace b200sort
+
+using namespace b200sort;
+
+extern "C" {
+
+const char *b200sort_version(void) { return "b200sort 0.1 (sm_100a)"; }
+
+const char *b200sort_status_string(int status) {
+    switch (status) {
+        case B200SORT_OK: return "ok";
+        case B200SORT_ERR_INVALID: return "invalid argument";
+        case B200SORT_ERR_WORKSPACE: return "workspace missing, misaligned or too small";
+        case B200SORT_ERR_CUDA: return "CUDA runtime error";
+        case B200SORT_ERR_NO_DEVICE: return "no sm_100 device (this library has no CPU fallback)";
+        case B200SORT_ERR_ALLOC: return "allocation failed";
+        default: return "unknown status";
+    }
+}
+
+int b200sort_last_cuda_error(void) { return (int)g_last_cuda_error; }
+const char *b200sort_last_cuda_error_string(void) { return cudaGetErrorString(g_last_cuda_error); }
+int b200sort_device_check(void) { return device_check(); }
+
+size_t b200sort_workspace_bytes(size_t n, int algo) { return workspace_bytes(n, algo); }
+
+int b200sort_radix_i32(int32_t *d_keys, int32_t *d_tmp, size_t n, void *d_ws, size_t ws_bytes, void *stream) {
+    B200_TRY(check_sort_args(d_keys, d_tmp, n));
+    return radix_sort(d_keys, d_keys, d_tmp, n, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int b200sort_merge_i32(int32_t *d_keys, int32_t *d_tmp, size_t n, void *d_ws, size_t ws_bytes, void *stream) {
+    B200_TRY(check_sort_args(d_keys, d_tmp, n));
+    return merge_sort(d_keys, d_keys, d_tmp, n, d_ws, ws_bytes, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int b200sort_sort_i32(int algo, int32_t *d_keys, int32_t *d_tmp, size_t n, void *d_ws, size_t ws_bytes,
+                      void *stream) {
+    B200_TRY(check_sort_args(d_keys, d_tmp, n));
+    return sort_dispatch(algo, d_keys, d_keys, d_tmp, n, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int b200sort_sort_copy_i32(int algo, const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n,
+                           void *d_ws, size_t ws_bytes, void *stream) {
+    B200_TRY(check_sort_args(d_out, d_tmp, n));
+    if (n > 0 && d_in == nullptr) return B200SORT_ERR_INVALID;
+    return sort_dispatch(algo, d_in, d_out, d_tmp, n, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int b200sort_sort_timed_i32(int algo, const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n,
+                            void *d_ws, size_t ws_bytes, void *stream, float *ms) {
+    B200_TRY(check_sort_args(d_out, d_tmp, n));
+    if ((n > 0 && d_in == nullptr) || ms == nullptr) return B200SORT_ERR_INVALID;
+    return sort_dispatch(algo, d_in, d_out, d_tmp, n, d_ws, ws_bytes, static_cast<cudaStream_t>(stream), ms);
+}
+
+int b200sort_radix_histogram_i32(const int32_t *d_keys, size_t n, uint32_t *d_hist, void *stream) {
+    if (d_hist == nullptr || (n > 0 && d_keys == nullptr) || n > B200SORT_MAX_N) return B200SORT_ERR_INVALID;
+    return radix_histogram(d_keys, n, d_hist, static_cast<cudaStream_t>(stream));
+}
+
+int b200sort_radix_pass_i32(const int32_t *d_in, int32_t *d_out, size_t n, int pass, void *d_ws,
+                            size_t ws_bytes, void *stream) {
+    if (n > B200SORT_MAX_N || (n > 0 && (d_in == nullptr || d_out == nullptr))) return B200SORT_ERR_INVALID;
+    return radix_single_pass(d_in, d_out, n, pass, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t b200sort_block_sort_tile(void) { return merge_block_tile(); }
+int b200sort_block_sort_i32(const int32_t *d_in, int32_t *d_out, size_t n, void *stream) {
+    if (n > B200SORT_MAX_N || (n > 0 && (d_in == nullptr || d_out == nullptr))) return B200SORT_ERR_INVALID;
+    return merge_block_sort(d_in, d_out, n, static_cast<cudaStream_t>(stream));
+}
+size_t b200sort_merge_tile(void) { return merge_tile(); }
+int b200sort_merge_partition_i32(const int32_t *d_in, size_t n, size_t run, uint32_t *d_splits, void *stream) {
+    if (n > B200SORT_MAX_N || (n > 0 && (d_in == nullptr || d_splits == nullptr))) return B200SORT_ERR_INVALID;
+    return merge_partition(d_in, n, run, d_splits, static_cast<cudaStream_t>(stream));
+}
+int b200sort_merge_pass_i32(const int32_t *d_in, int32_t *d_out, size_t n, size_t run,
+                            const uint32_t *d_splits, void *stream) {
+    if (n > B200SORT_MAX_N || (n > 0 && (d_in == nullptr || d_out == nullptr || d_splits == nullptr)))
+        return B200SORT_ERR_INVALID;
+    return merge_pass(d_in, d_out, n, run, d_splits, static_cast<cudaStream_t>(stream));
+}
+
+int b200sort_radix_set_variant(int variant) { return radix_set_variant(variant); }
+int b200sort_radix_num_variants(void) { return radix_num_variants(); }
+const char *b200sort_radix_variant_name(int variant) { return radix_variant_name(variant); }
+size_t b200sort_radix_tile(void) { return radix_current_tile(); }
+int b200sort_radix_set_skip(int enabled) { radix_set_skip(enabled); return B200SORT_OK; }
+unsigned long long b200sort_launch_count(void) { return g_launch_count; }
+void b200sort_launch_count_reset(void) { g_launch_count = 0; }
+
+int b200sort_order_array_host(int32_t *h_keys, size_t n, int algo) { return order_host(h_keys, n, algo); }
+int b200sort_order_with_trust_host(int32_t *h_keys, size_t n) {
+    return order_host(h_keys, n, B200SORT_ALGO_MERGE);
+}
+void b200sort_host_release(void) {
+    HostArena &a = arena();
+    std::lock_guard<std::mutex> lock(a.mu);
+    a.release();
+}
+int b200sort_host_alloc_pinned(void **h_ptr, size_t bytes) {
+    if (h_ptr == nullptr) return B200SORT_ERR_INVALID;
+    B200_CUDA_TRY(cudaMallocHost(h_ptr, bytes));
+    return B200SORT_OK;
+}
+int b200sort_host_free_pinned(void *h_ptr) {
+    B200_CUDA_TRY(cudaFreeHost(h_ptr));
+    return B200SORT_OK;
+}
+
+}  // extern "C"

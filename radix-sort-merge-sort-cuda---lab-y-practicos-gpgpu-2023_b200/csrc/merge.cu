@@ -1,0 +1,290 @@
+// merge.cu -- merge sort of int32 keys for sm_100a.
+//
+// Replaces the lab's merge stages (SRM/lab.cu:192-197 orderedJoin, :209-270 separators_kernel,
+// :272-300 merge_segments_kernel) with
+//
+//   k3  block_sort_kernel        one CTA sorts a tile of kBlockTile keys: a bitonic network on the
+//                                K keys each thread holds in registers, then log2(threads) rounds
+//                                of merge-path merging through shared memory.          8 B/key
+//   k4  merge_partition_kernel   one thread per output-tile boundary: diagonal binary search over
+//                                the two runs in global memory (replaces the separator ranking,
+//                                no 1024-thread / 48 KiB limit, no tail window).       O(n/T log n)
+//   k5  merge_pass_kernel        one CTA per output tile: stages its A- and B-slice in shared
+//                                memory, every thread merge-path-searches its K outputs and
+//                                merges them serially, coalesced store.                8 B/key
+//
+// Ties take from A first (the reference's rule, SRM/lab.cu:163-170); for keys-only data it is
+// invisible in the output but it keeps the partition consistent between k4 and k5.
+#include "merge.cuh"
+
+namespace b200sort {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortK       = 16;
+constexpr int kSortTile    = kSortThreads * kSortK;   // 4096
+
+// Shared-memory index skew: one pad word per 32 so that "thread t, item k" (stride K) and
+// "item j, thread t" (stride 1) are both conflict-free.
+__device__ __forceinline__ uint32_t pad(uint32_t i) { return i + (i >> 5); }
+// + K + 1: the serial merge reads one element ahead and, past the end of a ragged tile, up to K on.
+constexpr int kSortSmemWords = (kSortTile + kSortK + 1) + ((kSortTile + kSortK + 1) >> 5) + 1;
+
+__device__ __forceinline__ void cas(int32_t &a, int32_t &b, bool ascending) {
+    const bool sw = ascending ? (a > b) : (a < b);
+    const int32_t x = sw ? b : a, y = sw ? a : b;
+    a = x; b = y;
+}
+
+// Bitonic sorting network over K registers (all indices are compile-time after unrolling).
+template <int K>
+__device__ __forceinline__ void thread_bitonic_sort(int32_t (&key)[K]) {
+#pragma unroll
+    for (int k = 2; k <= K; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const int l = i ^ j;
+                if (l > i) cas(key[i], key[l], (i & k) == 0);
+            }
+        }
+    }
+}
+
+// Number of A elements among the first `diag` outputs of merge(A, B), A before equal B.
+// A = s[a_base .. a_base+la), B = s[b_base .. b_base+lb), padded indexing.
+__device__ __forceinline__ uint32_t merge_path_smem(const int32_t *s, uint32_t a_base, uint32_t la,
+                                                    uint32_t b_base, uint32_t lb, uint32_t diag) {
+    uint32_t lo = diag > lb ? diag - lb : 0, hi = diag < la ? diag : la;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const int32_t a = s[pad(a_base + mid)];
+        const int32_t b = s[pad(b_base + diag - 1 - mid)];
+        if (a <= b) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Serial merge of K outputs starting at (a_ptr, b_ptr); absolute padded-index pointers.
+template <int K>
+__device__ __forceinline__ void serial_merge(const int32_t *s, uint32_t a_ptr, uint32_t a_end,
+                                             uint32_t b_ptr, uint32_t b_end, int32_t (&out)[K]) {
+    int32_t a_val = s[pad(a_ptr)], b_val = s[pad(b_ptr)];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const bool take_a = (b_ptr >= b_end) || (a_ptr < a_end && a_val <= b_val);
+        out[k] = take_a ? a_val : b_val;
+        if (take_a) { ++a_ptr; a_val = s[pad(a_ptr)]; }
+        else        { ++b_ptr; b_val = s[pad(b_ptr)]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k3
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads)
+block_sort_kernel(const int32_t *in, int32_t *out, size_t n)
+{
+    __shared__ int32_t s[kSortSmemWords];
+    const uint32_t tid = threadIdx.x;
+    const size_t tile_base = (size_t)blockIdx.x * kSortTile;
+    const uint32_t valid = (n - tile_base < (size_t)kSortTile) ? (uint32_t)(n - tile_base) : (uint32_t)kSortTile;
+
+    // coalesced load; the tail is padded with INT_MAX, which sorts last
+#pragma unroll
+    for (int j = 0; j < kSortK; ++j) {
+        const uint32_t i = j * kSortThreads + tid;
+        s[pad(i)] = (i < valid) ? ld_stream(in + tile_base + i) : 0x7FFFFFFF;
+    }
+    if (tid == 0) { s[pad(kSortTile)] = 0x7FFFFFFF; }
+    __syncthreads();
+
+    int32_t key[kSortK];
+#pragma unroll
+    for (int k = 0; k < kSortK; ++k) key[k] = s[pad(tid * kSortK + k)];
+    thread_bitonic_sort<kSortK>(key);
+    __syncthreads();
+
+    // merge rounds: sorted runs of len -> 2*len
+#pragma unroll 1
+    for (uint32_t len = kSortK; len < (uint32_t)kSortTile; len <<= 1) {
+#pragma unroll
+        for (int k = 0; k < kSortK; ++k) s[pad(tid * kSortK + k)] = key[k];
+        __syncthreads();
+        const uint32_t first = tid * kSortK;
+        const uint32_t start = first & ~(2 * len - 1);
+        const uint32_t diag = first - start;
+        const uint32_t ai = merge_path_smem(s, start, len, start + len, len, diag);
+        serial_merge<kSortK>(s, start + ai, start + len, start + len + (diag - ai), start + 2 * len, key);
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int k = 0; k < kSortK; ++k) s[pad(tid * kSortK + k)] = key[k];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSortK; ++j) {
+        const uint32_t i = j * kSortThreads + tid;
+        if (i < valid) st_stream(out + tile_base + i, s[pad(i)]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k4
+// ------------------------------------------------------------------------------------------------
+struct PairGeom { size_t base; size_t la; size_t lb; };
+__device__ __forceinline__ PairGeom pair_of(size_t g, size_t n, size_t run) {
+    PairGeom p;
+    p.base = g / (2 * run) * (2 * run);
+    const size_t rest = n - p.base;
+    p.la = rest < run ? rest : run;
+    p.lb = rest - p.la < run ? rest - p.la : run;
+    return p;
+}
+
+__global__ void __launch_bounds__(128)
+merge_partition_kernel(const int32_t *__restrict__ in, size_t n, size_t run, uint32_t *splits,
+                       size_t num_tiles)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) {
+        if (t == num_tiles) splits[t] = 0;   // sentinel, never read as a start
+        return;
+    }
+    const size_t g = t * kSortTile;
+    const PairGeom p = pair_of(g, n, run);
+    const size_t diag = g - p.base;          // < la + lb because g < n
+    const int32_t *a = in + p.base, *b = a + p.la;
+    size_t lo = diag > p.lb ? diag - p.lb : 0, hi = diag < p.la ? diag : p.la;
+    while (lo < hi) {
+        const size_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) <= __ldg(b + diag - 1 - mid)) lo = mid + 1; else hi = mid;
+    }
+    splits[t] = (uint32_t)lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k5
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads)
+merge_pass_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, size_t n, size_t run,
+                  const uint32_t *__restrict__ splits)
+{
+    __shared__ int32_t s[kSortSmemWords];
+    const uint32_t tid = threadIdx.x;
+    const size_t t = blockIdx.x;
+    const size_t g0 = t * kSortTile;
+    const PairGeom p = pair_of(g0, n, run);
+    const size_t diag0 = g0 - p.base;
+    const size_t pair_len = p.la + p.lb;
+    const size_t diag1 = diag0 + kSortTile < pair_len ? diag0 + kSortTile : pair_len;
+    const size_t a0 = splits[t];
+    const size_t b0 = diag0 - a0;
+    const size_t a1 = (diag1 == pair_len) ? p.la : (size_t)splits[t + 1];
+    const size_t b1 = diag1 - a1;
+    const uint32_t na = (uint32_t)(a1 - a0), nb = (uint32_t)(b1 - b0), total = na + nb;
+
+    const int32_t *a = in + p.base + a0;
+    const int32_t *b = in + p.base + p.la + b0;
+#pragma unroll
+    for (int j = 0; j < kSortK; ++j) {
+        const uint32_t i = j * kSortThreads + tid;
+        int32_t v = 0x7FFFFFFF;
+        if (i < na) v = ld_stream(a + i);
+        else if (i < total) v = ld_stream(b + (i - na));
+        s[pad(i)] = v;
+    }
+    if (tid == 0) s[pad(kSortTile)] = 0x7FFFFFFF;
+    __syncthreads();
+
+    const uint32_t first = tid * kSortK;
+    const uint32_t diag = first < total ? first : total;
+    const uint32_t ai = merge_path_smem(s, 0, na, na, nb, diag);
+    int32_t key[kSortK];
+    serial_merge<kSortK>(s, ai, na, na + (diag - ai), total, key);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortK; ++k) s[pad(first + k)] = key[k];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSortK; ++j) {
+        const uint32_t i = j * kSortThreads + tid;
+        if (i < total) st_stream(out + g0 + i, s[pad(i)]);
+    }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+size_t merge_block_tile() { return kSortTile; }
+size_t merge_tile() { return kSortTile; }
+
+size_t merge_workspace_bytes(size_t n) {
+    return align_up((div_up(n > 0 ? n : 1, kSortTile) + 2) * sizeof(uint32_t), 256);
+}
+
+int merge_block_sort(const int32_t *d_in, int32_t *d_out, size_t n, cudaStream_t s) {
+    if (n == 0) return B200SORT_OK;
+    block_sort_kernel<<<(unsigned)div_up(n, kSortTile), kSortThreads, 0, s>>>(d_in, d_out, n);
+    B200_LAUNCH_CHECK();
+    return B200SORT_OK;
+}
+
+int merge_partition(const int32_t *d_in, size_t n, size_t run, uint32_t *d_splits, cudaStream_t s) {
+    if (n == 0) return B200SORT_OK;
+    if (run == 0 || run % kSortTile != 0) return B200SORT_ERR_INVALID;
+    const size_t tiles = div_up(n, kSortTile);
+    merge_partition_kernel<<<(unsigned)div_up(tiles + 1, 128), 128, 0, s>>>(d_in, n, run, d_splits, tiles);
+    B200_LAUNCH_CHECK();
+    return B200SORT_OK;
+}
+
+int merge_pass(const int32_t *d_in, int32_t *d_out, size_t n, size_t run, const uint32_t *d_splits,
+               cudaStream_t s) {
+    if (n == 0) return B200SORT_OK;
+    if (run == 0 || run % kSortTile != 0) return B200SORT_ERR_INVALID;
+    merge_pass_kernel<<<(unsigned)div_up(n, kSortTile), kSortThreads, 0, s>>>(d_in, d_out, n, run, d_splits);
+    B200_LAUNCH_CHECK();
+    return B200SORT_OK;
+}
+
+int merge_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, void *d_ws,
+               size_t ws_bytes, cudaStream_t s, float *ms) {
+    if (ms) ms[0] = ms[1] = ms[2] = 0.f;
+    if (n == 0) return B200SORT_OK;
+    if (n == 1) {
+        if (d_in != d_out) B200_CUDA_TRY(cudaMemcpyAsync(d_out, d_in, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        return B200SORT_OK;
+    }
+    if (d_ws == nullptr || ws_bytes < merge_workspace_bytes(n)) return B200SORT_ERR_WORKSPACE;
+    auto *splits = static_cast<uint32_t *>(d_ws);
+    int passes = 0;
+    for (size_t run = kSortTile; run < n; run *= 2) ++passes;
+    // Land the final pass in d_out: the block sort (which may run in place) writes to whichever
+    // buffer makes that so.  d_in is only ever read by the block sort.
+    int32_t *src = (passes % 2 == 0) ? d_out : d_tmp;
+    int32_t *dst = (passes % 2 == 0) ? d_tmp : d_out;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (ms) {
+        for (auto &e : ev) B200_CUDA_TRY(cudaEventCreate(&e));
+        B200_CUDA_TRY(cudaEventRecord(ev[0], s));
+    }
+    B200_TRY(merge_block_sort(d_in, src, n, s));
+    if (ms) B200_CUDA_TRY(cudaEventRecord(ev[1], s));
+    for (size_t run = kSortTile; run < n; run *= 2) {
+        B200_TRY(merge_partition(src, n, run, splits, s));
+        B200_TRY(merge_pass(src, dst, n, run, splits, s));
+        int32_t *t = src; src = dst; dst = t;
+    }
+    if (ms) {
+        B200_CUDA_TRY(cudaEventRecord(ev[2], s));
+        B200_CUDA_TRY(cudaEventSynchronize(ev[2]));
+        B200_CUDA_TRY(cudaEventElapsedTime(&ms[0], ev[0], ev[1]));   // block sort
+        B200_CUDA_TRY(cudaEventElapsedTime(&ms[1], ev[1], ev[2]));   // all merge passes
+        ms[2] = (float)passes;
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
+    return B200SORT_OK;
+}
+
+}  // namespace b200sort
