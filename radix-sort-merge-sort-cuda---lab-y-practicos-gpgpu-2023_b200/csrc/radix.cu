@@ -25,17 +25,41 @@ namespace b200sort {
 // k1: digit histograms
 // ================================================================================================
 constexpr int kHistThreads = 512;
-constexpr int kHistRepl    = 8;                  // replicated counters: lane % 8 picks a replica
-constexpr int kHistRow     = kRadixBins + 1;     // 257 words: replica r sits r banks further on
 constexpr int kHistUnroll  = 4;                  // 128-bit loads in flight per thread
 constexpr int kHistBlocksPerSM = 3;
+// Shared-memory counters are 16-bit and LANE-PRIVATE: counter (place p, digit d, lane l) lives in
+// half (l & 1) of word (p*256 + d)*16 + (l >> 1).  The bank is 16*(d & 1) + (l >> 1), so the only
+// lanes that can ever collide in one atomic instruction are the two lanes of a pair -- at most
+// 2 wavefronts whatever the key distribution (32 random words on 32 banks cost ~3.5, and an
+// all-equal input would serialise 32 ways).  16-bit counters overflow after 65535 hits, so the
+// block flushes to the global histogram every kHistFlushIters iterations (<= 32768 hits each).
+constexpr int kHistSmemWords  = kRadixPasses * kRadixBins * 16;                  // 64 KiB
+constexpr size_t kHistSmemBytes = (size_t)kHistSmemWords * 4;
+constexpr int kHistFlushIters = 128;   // 128 iters * (4 keys * 4 loads) * 16 warps = 32768 per lane column
 
-__device__ __forceinline__ void hist_add(uint32_t *my, int32_t key) {
+__device__ __forceinline__ void hist_add(uint32_t *col, uint32_t one, int32_t key) {
     const uint32_t k = key_bits(key);
-    atomicAdd(my + 0 * kHistRow + (k & 255u), 1u);
-    atomicAdd(my + 1 * kHistRow + ((k >> 8) & 255u), 1u);
-    atomicAdd(my + 2 * kHistRow + ((k >> 16) & 255u), 1u);
-    atomicAdd(my + 3 * kHistRow + (k >> 24), 1u);
+    atomicAdd(col + (0 * kRadixBins + (k & 255u)) * 16, one);
+    atomicAdd(col + (1 * kRadixBins + ((k >> 8) & 255u)) * 16, one);
+    atomicAdd(col + (2 * kRadixBins + ((k >> 16) & 255u)) * 16, one);
+    atomicAdd(col + (3 * kRadixBins + (k >> 24)) * 16, one);
+}
+
+// Sum the 32 lane columns of every (place, digit), add into the global histogram, clear.
+__device__ __forceinline__ void hist_flush(uint32_t *sh, RadixControl *ctl, uint32_t tid) {
+    __syncthreads();
+    for (uint32_t i = tid; i < kRadixPasses * kRadixBins; i += kHistThreads) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < 16; ++w) {
+            const uint32_t idx = i * 16 + ((w + (i >> 1)) & 15);   // rotate: conflict-free across threads
+            const uint32_t v = sh[idx];
+            sh[idx] = 0;
+            sum += (v & 0xffffu) + (v >> 16);
+        }
+        if (sum) atomicAdd(&ctl->hist[i >> kRadixBits][i & (kRadixBins - 1)], sum);
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(kHistThreads)
@@ -43,13 +67,16 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
                        uint32_t *status_to_zero, size_t status_words, uint32_t skip_enabled,
                        uint32_t in_place)
 {
-    __shared__ uint32_t sh[kHistRepl * kRadixPasses * kHistRow];
+    extern __shared__ __align__(16) uint32_t sh[];
     __shared__ uint32_t s_warp_sums[kRadixBins / 32];
     __shared__ uint32_t s_skip[kRadixPasses];
     __shared__ uint32_t s_is_last;
 
     const uint32_t tid = threadIdx.x;
-    for (uint32_t i = tid; i < kHistRepl * kRadixPasses * kHistRow; i += kHistThreads) sh[i] = 0;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(sh);
+        for (uint32_t i = tid; i < kHistSmemWords / 4; i += kHistThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
 
     // Zero the tile-status buffer the first pass will use.
     if (status_to_zero != nullptr) {
@@ -61,7 +88,8 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
     }
     __syncthreads();
 
-    uint32_t *my = sh + (tid % kHistRepl) * (kRadixPasses * kHistRow);
+    uint32_t *col = sh + ((tid & 31) >> 1);
+    const uint32_t one = 1u << (16 * (tid & 1));
 
     // Scalar head up to 16-byte alignment, 128-bit body, scalar tail.
     size_t head = ((16 - (reinterpret_cast<uintptr_t>(keys) & 15)) & 15) / 4;
@@ -71,6 +99,7 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
     const int4 *v = reinterpret_cast<const int4 *>(keys + head);
 
     constexpr size_t kChunk = (size_t)kHistThreads * kHistUnroll;
+    int iters = 0;
     for (size_t base = (size_t)blockIdx.x * kChunk; base < nvec; base += (size_t)gridDim.x * kChunk) {
         int4 r[kHistUnroll];
         bool ok[kHistUnroll];
@@ -83,25 +112,17 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
 #pragma unroll
         for (int u = 0; u < kHistUnroll; ++u) {
             if (ok[u]) {
-                hist_add(my, r[u].x); hist_add(my, r[u].y);
-                hist_add(my, r[u].z); hist_add(my, r[u].w);
+                hist_add(col, one, r[u].x); hist_add(col, one, r[u].y);
+                hist_add(col, one, r[u].z); hist_add(col, one, r[u].w);
             }
         }
+        if (++iters == kHistFlushIters) { hist_flush(sh, ctl, tid); iters = 0; }
     }
-    if (blockIdx.x == 0) {
-        for (size_t i = tid; i < head; i += kHistThreads) hist_add(my, keys[i]);
-        for (size_t i = tail_start + tid; i < n; i += kHistThreads) hist_add(my, keys[i]);
+    if (blockIdx.x == 0) {   // < 8 keys in total: cannot overflow anything
+        for (size_t i = tid; i < head; i += kHistThreads) hist_add(col, one, keys[i]);
+        for (size_t i = tail_start + tid; i < n; i += kHistThreads) hist_add(col, one, keys[i]);
     }
-    __syncthreads();
-
-    // Fold the replicas and add into the global histogram.
-    for (uint32_t i = tid; i < kRadixPasses * kRadixBins; i += kHistThreads) {
-        const uint32_t p = i >> kRadixBits, d = i & (kRadixBins - 1);
-        uint32_t sum = 0;
-#pragma unroll
-        for (int r = 0; r < kHistRepl; ++r) sum += sh[(r * kRadixPasses + p) * kHistRow + d];
-        if (sum) atomicAdd(&ctl->hist[p][d], sum);
-    }
+    hist_flush(sh, ctl, tid);
 
     // The last block to finish turns counts into exclusive bases.
     __threadfence();
@@ -166,34 +187,48 @@ constexpr uint32_t kFlagLocal = 1u << 30;   // this tile's own digit count
 constexpr uint32_t kFlagIncl  = 2u << 30;   // inclusive count over tiles 0..this
 constexpr uint32_t kValueMask = (1u << 30) - 1;
 
-template <int WARPS, int IPT>
+// How a warp finds, for each of its 32 current keys, the lanes holding the same digit:
+//   kRankMatch   __match_any_sync (one MATCH instruction; runs on the ADU pipe)
+//   kRankBallot  eight __ballot_sync, one per digit bit (VOTE + LOP3, no shared memory)
+//   kRankAtomic  atomicOr of the lane bit into a per-warp {peer mask, count} table in shared memory
+enum RankMode { kRankMatch = 0, kRankBallot = 1, kRankAtomic = 2 };
+
+template <int WARPS, int IPT, int MODE>
 struct OnesweepShape {
     static constexpr int kThreads = WARPS * 32;
     static constexpr int kTile    = kThreads * IPT;
+    static constexpr int kTableWords = (MODE == kRankAtomic) ? 2 : 1;   // words per (warp, digit)
     static constexpr size_t kSmemBytes =
-        (size_t)WARPS * kRadixBins * 4      // per-warp digit counters -> per-warp offsets
-        + (size_t)kTile * 4                 // keys staged in digit order
-        + (size_t)kRadixBins * 4 * 2        // tile_start, global offset
-        + 64;                               // warp sums, tile id
+        (size_t)WARPS * kRadixBins * 4 * kTableWords   // per-warp digit counters -> offsets
+        + (size_t)kTile * 4                            // keys staged in digit order
+        + (size_t)kRadixBins * 4                       // global offset per digit
+        + 64;                                          // warp sums, tile id
 };
 
-template <int WARPS, int IPT, int MIN_BLOCKS>
+// digit of `key` for the pass with this shift; `flip` is 0x80 for the top digit (signed order)
+__device__ __forceinline__ uint32_t digit_of(int32_t key, int shift, uint32_t flip) {
+    return ((static_cast<uint32_t>(key) >> shift) & (kRadixBins - 1)) ^ flip;
+}
+
+template <int WARPS, int IPT, int MIN_BLOCKS, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
 radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n, int pass,
                       RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
                       int follow_plan)
 {
-    using Shape = OnesweepShape<WARPS, IPT>;
+    using Shape = OnesweepShape<WARPS, IPT, MODE>;
     constexpr int kThreads = Shape::kThreads;
     constexpr int kTile    = Shape::kTile;
+    constexpr int TW       = Shape::kTableWords;
     static_assert(WARPS >= kRadixBins / 32, "need one thread per digit");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *s_warp_hist  = reinterpret_cast<uint32_t *>(smem_raw);              // [WARPS][256]
-    int32_t  *s_keys       = reinterpret_cast<int32_t *>(s_warp_hist + WARPS * kRadixBins);
-    uint32_t *s_tile_start = reinterpret_cast<uint32_t *>(s_keys + kTile);        // [256]
-    uint32_t *s_gofs       = s_tile_start + kRadixBins;                           // [256]
-    uint32_t *s_misc       = s_gofs + kRadixBins;                                 // [16]
+    // [WARPS][256] entries of TW words.  Entry word TW-1 is the running count, later the offset
+    // of (warp, digit) inside the staged tile; with kRankAtomic word 0 is the peer mask.
+    uint32_t *s_table = reinterpret_cast<uint32_t *>(smem_raw);
+    int32_t  *s_keys  = reinterpret_cast<int32_t *>(s_table + WARPS * kRadixBins * TW);
+    uint32_t *s_gofs  = reinterpret_cast<uint32_t *>(s_keys + kTile);             // [256]
+    uint32_t *s_misc  = s_gofs + kRadixBins;                                      // [16]
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -214,13 +249,17 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
 
     // Tiles are handed out by ticket so that a tile only ever waits on tiles already running.
     if (tid == 0) s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(s_table + warp * kRadixBins * TW);
 #pragma unroll
-    for (int j = lane; j < kRadixBins; j += 32) s_warp_hist[warp * kRadixBins + j] = 0;
+        for (int j = lane; j < kRadixBins * TW / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
     const uint32_t tile = s_misc[8];
     const size_t tile_base = (size_t)tile * kTile;
     const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
     const int shift = pass * kRadixBits;
+    const uint32_t flip = (pass == kRadixPasses - 1) ? 0x80u : 0u;
 
     // ---- load, warp-striped: item i of lane l is key warp*32*IPT + i*32 + l of the tile ---------
     int32_t key[IPT];
@@ -237,41 +276,61 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
         }
     }
 
-    // ---- rank inside the warp: peers with my digit, in lane order ----------------------------
-    uint32_t rank[IPT];
+    // ---- rank inside the warp: earlier keys of this warp with my digit ----------------------------
+    // (two 16-bit ranks per register: a warp holds at most 32*IPT < 65536 keys)
+    static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in pairs");
+    uint32_t rank2[IPT / 2];
     {
-        uint32_t *wh = s_warp_hist + warp * kRadixBins;
+        uint32_t *wt = s_table + warp * kRadixBins * TW;
         const uint32_t lt = lanemask_lt();
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
-            const uint32_t d = (key_bits(key[i]) >> shift) & (kRadixBins - 1);
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            const uint32_t leader = __ffs(peers) - 1;
-            uint32_t before = 0;
-            if (lane == leader) {
-                before = wh[d];
-                wh[d] = before + __popc(peers);
+            const uint32_t d = digit_of(key[i], shift, flip);
+            if (MODE == kRankAtomic) {
+                atomicOr(wt + 2 * d, 1u << lane);
+                __syncwarp();
+                const uint2 e = *reinterpret_cast<const uint2 *>(wt + 2 * d);   // {peers, count}
+                const uint32_t lower = e.x & lt;
+                const uint32_t r = e.y + __popc(lower);
+                rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
+                __syncwarp();
+                if (lower == 0)                                                   // lowest peer
+                    *reinterpret_cast<uint2 *>(wt + 2 * d) = make_uint2(0u, e.y + __popc(e.x));
+                __syncwarp();
+            } else {
+                uint32_t peers;
+                if (MODE == kRankMatch) {
+                    peers = __match_any_sync(0xffffffffu, d);
+                } else {
+                    peers = 0xffffffffu;
+#pragma unroll
+                    for (int b = 0; b < kRadixBits; ++b) {
+                        const bool bit = (d >> b) & 1u;
+                        const uint32_t vote = __ballot_sync(0xffffffffu, bit);
+                        peers &= bit ? vote : ~vote;
+                    }
+                }
+                const uint32_t lower = peers & lt;
+                uint32_t before = 0;
+                if (lower == 0) before = atomicAdd(wt + d, (uint32_t)__popc(peers));   // one lane per digit
+                before = __shfl_sync(0xffffffffu, before, __ffs(peers) - 1);
+                const uint32_t r = before + __popc(lower);
+                rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
             }
-            before = __shfl_sync(0xffffffffu, before, leader);
-            rank[i] = before + __popc(peers & lt);
-            __syncwarp();
         }
     }
     __syncthreads();
 
-    // ---- per digit: warp counts -> warp offsets, tile total; publish; scan over digits ---------
+    // ---- per digit: tile total over the warps; publish it; exclusive scan over the digits ---------
     uint32_t total = 0;
     if (tid < kRadixBins) {
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const uint32_t c = s_warp_hist[w * kRadixBins + tid];
-            s_warp_hist[w * kRadixBins + tid] = total;
-            total += c;
-        }
-        uint32_t *slot = status_cur + (size_t)tile * kRadixBins + tid;
-        st_relaxed_gpu(slot, (tile == 0 ? kFlagIncl : kFlagLocal) | total);
+        for (int w = 0; w < WARPS; ++w) total += s_table[(w * kRadixBins + tid) * TW + (TW - 1)];
+        st_relaxed_gpu(status_cur + (size_t)tile * kRadixBins + tid,
+                       (tile == 0 ? kFlagIncl : kFlagLocal) | total);
         if (status_next != nullptr) status_next[(size_t)tile * kRadixBins + tid] = 0;
     }
+    uint32_t tile_start = 0;
     {
         uint32_t x = total;   // threads >= 256 carry 0
 #pragma unroll
@@ -285,7 +344,16 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             uint32_t add = 0;
 #pragma unroll
             for (int w = 0; w < kRadixBins / 32; ++w) add += (w < (int)warp) ? s_misc[w] : 0u;
-            s_tile_start[tid] = x - total + add;
+            tile_start = x - total + add;
+            // warp counts -> position of (warp, digit) inside the staged tile
+            uint32_t run = tile_start;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                uint32_t *e = s_table + (w * kRadixBins + tid) * TW + (TW - 1);
+                const uint32_t c = *e;
+                *e = run;
+                run += c;
+            }
         }
     }
     __syncthreads();
@@ -293,8 +361,9 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     // ---- stage the keys in shared memory in digit order ---------------------------------------------
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-        const uint32_t d = (key_bits(key[i]) >> shift) & (kRadixBins - 1);
-        s_keys[s_tile_start[d] + s_warp_hist[warp * kRadixBins + d] + rank[i]] = key[i];
+        const uint32_t d = digit_of(key[i], shift, flip);
+        const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
+        s_keys[s_table[(warp * kRadixBins + d) * TW + (TW - 1)] + r] = key[i];
     }
 
     // ---- decoupled look-back: one thread per digit walks the predecessors' status words ------------
@@ -313,18 +382,26 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             st_relaxed_gpu(status_cur + (size_t)tile * kRadixBins + tid,
                            kFlagIncl | ((prev + total) & kValueMask));
         }
-        s_gofs[tid] = ctl->base[pass][tid] + prev - s_tile_start[tid];
+        s_gofs[tid] = ctl->base[pass][tid] + prev - tile_start;
     }
     __syncthreads();
 
     // ---- scatter: consecutive threads write consecutive addresses inside each digit run -----------
+    if (valid == (uint32_t)kTile) {
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-        const uint32_t p = tid + j * kThreads;
-        if (p < valid) {
+        for (int j = 0; j < IPT; ++j) {
+            const uint32_t p = tid + j * kThreads;
             const int32_t k = s_keys[p];
-            const uint32_t d = (key_bits(k) >> shift) & (kRadixBins - 1);
-            st_stream(out + (size_t)(uint32_t)(s_gofs[d] + p), k);
+            st_stream(out + (size_t)(uint32_t)(s_gofs[digit_of(k, shift, flip)] + p), k);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const uint32_t p = tid + j * kThreads;
+            if (p < valid) {
+                const int32_t k = s_keys[p];
+                st_stream(out + (size_t)(uint32_t)(s_gofs[digit_of(k, shift, flip)] + p), k);
+            }
         }
     }
 }
@@ -369,19 +446,24 @@ struct Variant {
     OnesweepFn fn;
 };
 
-#define B200_VARIANT(W, I, B)                                                            \
-    { "warps" #W "_ipt" #I "_occ" #B, OnesweepShape<W, I>::kThreads, OnesweepShape<W, I>::kTile, \
-      OnesweepShape<W, I>::kSmemBytes, radix_onesweep_kernel<W, I, B> }
+#define B200_VARIANT(W, I, B, M)                                                                    \
+    { "warps" #W "_ipt" #I "_occ" #B "_" #M, OnesweepShape<W, I, M>::kThreads,                      \
+      OnesweepShape<W, I, M>::kTile, OnesweepShape<W, I, M>::kSmemBytes,                            \
+      radix_onesweep_kernel<W, I, B, M> }
 
 const Variant kVariants[] = {
-    B200_VARIANT(16, 16, 2),   // 8192-key tiles, 2 CTAs/SM                (default)
-    B200_VARIANT(8, 16, 4),    // 4096-key tiles, 4 CTAs/SM
-    B200_VARIANT(16, 12, 2),   // 6144
-    B200_VARIANT(8, 24, 3),    // 6144, fewer threads
-    B200_VARIANT(12, 16, 3),   // 6144, 384 threads
-    B200_VARIANT(16, 20, 2),   // 10240
-    B200_VARIANT(8, 8, 6),     // 2048 (small-n friendly)
-    B200_VARIANT(16, 24, 1),   // 12288, 1 CTA/SM, most registers
+    B200_VARIANT(16, 16, 2, kRankBallot),   // 8192-key tiles, 2 CTAs/SM        (default)
+    B200_VARIANT(16, 16, 2, kRankAtomic),
+    B200_VARIANT(16, 16, 2, kRankMatch),
+    B200_VARIANT(8, 24, 3, kRankBallot),    // 6144, fewer threads
+    B200_VARIANT(8, 24, 3, kRankAtomic),
+    B200_VARIANT(16, 20, 2, kRankBallot),   // 10240
+    B200_VARIANT(16, 20, 2, kRankAtomic),
+    B200_VARIANT(8, 16, 4, kRankBallot),    // 4096-key tiles, 4 CTAs/SM
+    B200_VARIANT(8, 16, 4, kRankAtomic),
+    B200_VARIANT(8, 8, 6, kRankBallot),     // 2048 (small-n friendly)
+    B200_VARIANT(12, 16, 3, kRankBallot),   // 6144, 384 threads
+    B200_VARIANT(12, 20, 2, kRankBallot),   // 7680
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -395,6 +477,16 @@ int ensure_smem_attr(int v) {
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kVariants[v].smem));
         g_attrs_set[v].store(true, std::memory_order_release);
+    }
+    return B200SORT_OK;
+}
+
+std::atomic<bool> g_hist_attr_set{false};
+int ensure_hist_attr() {
+    if (!g_hist_attr_set.load(std::memory_order_acquire)) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_histogram_kernel),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHistSmemBytes));
+        g_hist_attr_set.store(true, std::memory_order_release);
     }
     return B200SORT_OK;
 }
@@ -428,9 +520,10 @@ int radix_histogram(const int32_t *d_keys, size_t n, uint32_t *d_hist, cudaStrea
     // block that lives in a small static device allocation.
     static thread_local RadixControl *scratch = nullptr;
     if (scratch == nullptr) B200_CUDA_TRY(cudaMalloc(&scratch, kRadixControlBytes));
+    B200_TRY(ensure_hist_attr());
     B200_CUDA_TRY(cudaMemsetAsync(scratch, 0, kRadixZeroBytes, s));
     if (n > 0) {
-        radix_histogram_kernel<<<hist_grid(n), kHistThreads, 0, s>>>(d_keys, n, scratch, nullptr, 0, 0, 0);
+        radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_keys, n, scratch, nullptr, 0, 0, 0);
         B200_LAUNCH_CHECK();
     }
     B200_CUDA_TRY(cudaMemcpyAsync(d_hist, scratch->hist, sizeof(uint32_t) * kRadixPasses * kRadixBins,
@@ -451,12 +544,13 @@ int radix_single_pass(const int32_t *d_in, int32_t *d_out, size_t n, int pass, v
     B200_TRY(check_ws(d_ws, ws_bytes, n));
     const int v = g_variant.load();
     B200_TRY(ensure_smem_attr(v));
+    B200_TRY(ensure_hist_attr());
     const Variant &var = kVariants[v];
     auto *ctl = static_cast<RadixControl *>(d_ws);
     auto *status0 = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(d_ws) + kRadixControlBytes);
     const size_t tiles = div_up(n, (size_t)var.tile);
     B200_CUDA_TRY(cudaMemsetAsync(ctl, 0, kRadixZeroBytes, s));
-    radix_histogram_kernel<<<hist_grid(n), kHistThreads, 0, s>>>(d_in, n, ctl, status0,
+    radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_in, n, ctl, status0,
                                                                  tiles * kRadixBins, 0, 0);
     B200_LAUNCH_CHECK();
     var.fn<<<(unsigned)tiles, var.threads, var.smem, s>>>(d_in, d_out, nullptr, n, pass, ctl, status0,
@@ -502,6 +596,7 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
     B200_TRY(check_ws(d_ws, ws_bytes, n));
     const int v = g_variant.load();
     B200_TRY(ensure_smem_attr(v));
+    B200_TRY(ensure_hist_attr());
     const Variant &var = kVariants[v];
     auto *ctl = static_cast<RadixControl *>(d_ws);
     const size_t tiles = div_up(n, (size_t)var.tile);
@@ -514,7 +609,7 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
 
     B200_CUDA_TRY(cudaMemsetAsync(ctl, 0, kRadixZeroBytes, s));
     B200_TRY(timer.begin());
-    radix_histogram_kernel<<<hist_grid(n), kHistThreads, 0, s>>>(d_in, n, ctl, status[0], tiles * kRadixBins,
+    radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_in, n, ctl, status[0], tiles * kRadixBins,
                                                                  (uint32_t)skip, in_place);
     B200_LAUNCH_CHECK();
     B200_TRY(timer.mark());
