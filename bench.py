@@ -336,7 +336,8 @@ def ours_single(args) -> None:
                    "algo": args.algo, "dist": args.dist, "seed": 1, "n": n,
                    "form": "out-of-place (b200sort_sort_copy_i32): each step sorts the same pristine input",
                    "l2": "inputs larger than L2 (1 GiB input vs 126 MB L2), no explicit flush",
-                   "radix_variant": L.b200sort_radix_variant_name(args.variant or 0).decode(),
+                   "radix_variant": L.b200sort_radix_effective_variant_name().decode(),
+                   "atomic_order_selftest": bool(L.b200sort_radix_atomic_order_ok()),
                    "radix_tile": int(L.b200sort_radix_tile())},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "clocks": sampler.summary(t0, t1),

@@ -118,6 +118,14 @@ int         b200sort_radix_set_variant(int variant);
 int         b200sort_radix_num_variants(void);
 const char *b200sort_radix_variant_name(int variant);
 size_t      b200sort_radix_tile(void);            /* keys per onesweep tile of the current variant */
+/* The fastest tile shapes rank keys with one shared-memory atomicAdd per key, which is a stable
+ * rank only if the GPU resolves same-address lanes of one warp instruction in lane order.  That is
+ * observed on B200 but not promised by PTX, so the library runs a self-test once per process
+ * (BLOCKS on first call; needs a device) and otherwise launches the ballot-ranked shape instead.
+ * Returns 1 (ordered: fast shapes in use) or 0.  B200SORT_RANK_SAFE=1 in the environment forces 0. */
+int         b200sort_radix_atomic_order_ok(void);
+/* Name of the shape that will actually be launched (after the self-test's verdict). */
+const char *b200sort_radix_effective_variant_name(void);
 /* Pass skipping: when a digit histogram shows one bin holding every key the pass is the
  * identity and is skipped on the device (no host sync).  1 = on (default), 0 = off. */
 int         b200sort_radix_set_skip(int enabled);

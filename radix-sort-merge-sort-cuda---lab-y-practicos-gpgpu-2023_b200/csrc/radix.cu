@@ -18,6 +18,7 @@
 #include "radix.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace b200sort {
 
@@ -191,7 +192,9 @@ constexpr uint32_t kValueMask = (1u << 30) - 1;
 //   kRankMatch   __match_any_sync (one MATCH instruction; runs on the ADU pipe)
 //   kRankBallot  eight __ballot_sync, one per digit bit (VOTE + LOP3, no shared memory)
 //   kRankAtomic  atomicOr of the lane bit into a per-warp {peer mask, count} table in shared memory
-enum RankMode { kRankMatch = 0, kRankBallot = 1, kRankAtomic = 2 };
+//   kRankAdd     EXPERIMENT: plain atomicAdd, stable only if the hardware resolves same-address
+//                lanes of one instruction in lane order (undocumented)
+enum RankMode { kRankMatch = 0, kRankBallot = 1, kRankAtomic = 2, kRankAdd = 3 };
 
 template <int WARPS, int IPT, int MODE>
 struct OnesweepShape {
@@ -201,7 +204,7 @@ struct OnesweepShape {
     static constexpr size_t kSmemBytes =
         (size_t)WARPS * kRadixBins * 4 * kTableWords   // per-warp digit counters -> offsets
         + (size_t)kTile * 4                            // keys staged in digit order
-        + (size_t)kRadixBins * 4                       // global offset per digit
+        + (size_t)kRadixBins * 4 * 3                   // global offset, tile total, tile start per digit
         + 64;                                          // warp sums, tile id
 };
 
@@ -286,7 +289,10 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const uint32_t d = digit_of(key[i], shift, flip);
-            if (MODE == kRankAtomic) {
+            if (MODE == kRankAdd) {
+                const uint32_t r = atomicAdd(wt + d, 1u);
+                rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
+            } else if (MODE == kRankAtomic) {
                 atomicOr(wt + 2 * d, 1u << lane);
                 __syncwarp();
                 const uint2 e = *reinterpret_cast<const uint2 *>(wt + 2 * d);   // {peers, count}
@@ -321,42 +327,106 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     }
     __syncthreads();
 
-    // ---- per digit: tile total over the warps; publish it; exclusive scan over the digits ---------
-    uint32_t total = 0;
-    if (tid < kRadixBins) {
+    // ---- per digit, two thread groups working side by side --------------------------------------
+    //   group A (threads 0..255, thread = digit): tile totals, exclusive scan over the digits,
+    //           warp counts -> positions inside the staged tile;
+    //   group B (threads 256..511, thread - 256 = digit; the same threads as A when the CTA has
+    //           fewer than 16 warps): publish the tile total, decoupled look-back over the
+    //           predecessor tiles with kLookWindow status words in flight per thread, publish the
+    //           inclusive count, global offset of the digit.
+    // Status words only ever move 0 -> local -> inclusive, so a stale (prefetched) read is safe.
+    // Named barriers: 1 = inside group A; 2 = "totals are in shared memory" (A arrives, B waits);
+    //                 3 = "positions are final" (A arrives, B waits).
+    constexpr bool kSplit = (WARPS >= 16);
+    constexpr int kLookWindow = 8;
+    uint32_t *s_total = s_misc + 16;                         // [256]
+    uint32_t *s_tstart = s_total + kRadixBins;               // [256]
+
+    const bool in_a = tid < kRadixBins;
+    const bool in_b = kSplit ? (tid >= kRadixBins && tid < 2 * kRadixBins) : in_a;
+    const uint32_t bd = kSplit ? tid - kRadixBins : tid;     // group B's digit
+    const uint32_t *look = status_cur + (size_t)tile * kRadixBins + bd;   // my digit in my tile's row
+
+    uint32_t win[kLookWindow];
+    if (kSplit && in_b) {
+        // first window, issued before anything else so that it overlaps group A's work
+#pragma unroll
+        for (int j = 0; j < kLookWindow; ++j)
+            win[j] = (tile >= (uint32_t)(j + 1)) ? ld_relaxed_gpu(look - (size_t)(j + 1) * kRadixBins)
+                                                 : kFlagIncl;            // before tile 0: inclusive 0
+    }
+    if (in_a) {
+        uint32_t total = 0;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) total += s_table[(w * kRadixBins + tid) * TW + (TW - 1)];
-        st_relaxed_gpu(status_cur + (size_t)tile * kRadixBins + tid,
-                       (tile == 0 ? kFlagIncl : kFlagLocal) | total);
-        if (status_next != nullptr) status_next[(size_t)tile * kRadixBins + tid] = 0;
-    }
-    uint32_t tile_start = 0;
-    {
-        uint32_t x = total;   // threads >= 256 carry 0
+        s_total[tid] = total;
+        if (kSplit) { __threadfence_block(); asm volatile("bar.arrive 2, 512;" ::: "memory"); }
+        uint32_t x = total;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
             if (lane >= (uint32_t)o) x += y;
         }
-        if (tid < kRadixBins && lane == 31) s_misc[warp] = x;
-        __syncthreads();
-        if (tid < kRadixBins) {
-            uint32_t add = 0;
+        if (lane == 31) s_misc[warp] = x;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        uint32_t add = 0;
 #pragma unroll
-            for (int w = 0; w < kRadixBins / 32; ++w) add += (w < (int)warp) ? s_misc[w] : 0u;
-            tile_start = x - total + add;
-            // warp counts -> position of (warp, digit) inside the staged tile
-            uint32_t run = tile_start;
+        for (int w = 0; w < kRadixBins / 32; ++w) add += (w < (int)warp) ? s_misc[w] : 0u;
+        const uint32_t tile_start = x - total + add;
+        uint32_t run = tile_start;
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) {
-                uint32_t *e = s_table + (w * kRadixBins + tid) * TW + (TW - 1);
-                const uint32_t c = *e;
-                *e = run;
-                run += c;
-            }
+        for (int w = 0; w < WARPS; ++w) {
+            uint32_t *e = s_table + (w * kRadixBins + tid) * TW + (TW - 1);
+            const uint32_t c = *e;
+            *e = run;
+            run += c;
         }
+        s_tstart[tid] = tile_start;
+        if (kSplit) { __threadfence_block(); asm volatile("bar.arrive 3, 512;" ::: "memory"); }
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // every (warp, digit) position is final
     }
-    __syncthreads();
+    if (in_b) {
+        if (kSplit) asm volatile("bar.sync 2, 512;" ::: "memory");
+        const uint32_t total = s_total[bd];
+        st_relaxed_gpu(const_cast<uint32_t *>(look), (tile == 0 ? kFlagIncl : kFlagLocal) | total);
+        if (status_next != nullptr) status_next[(size_t)tile * kRadixBins + bd] = 0;
+        uint32_t prev = 0;
+        if (tile > 0) {
+            uint32_t back = 1;                               // distance of the window's first tile
+            bool have = kSplit;                              // window already loaded?
+            for (;;) {
+                if (!have) {
+#pragma unroll
+                    for (int j = 0; j < kLookWindow; ++j)
+                        win[j] = (tile >= back + j) ? ld_relaxed_gpu(look - (size_t)(back + j) * kRadixBins)
+                                                    : kFlagIncl;
+                }
+                have = false;
+                bool done = false;
+                uint32_t used = 0;
+#pragma unroll
+                for (int j = 0; j < kLookWindow; ++j) {
+                    if (!done && used == (uint32_t)j) {
+                        const uint32_t f = win[j] & ~kValueMask;
+                        if (f != 0) {                        // published: take it
+                            prev += win[j] & kValueMask;
+                            used = j + 1;
+                            done = (f == kFlagIncl);
+                        }
+                    }
+                }
+                if (done) break;
+                back += used;                                // re-poll from the first unpublished tile
+            }
+            st_relaxed_gpu(const_cast<uint32_t *>(look), kFlagIncl | ((prev + total) & kValueMask));
+        }
+        if (kSplit) asm volatile("bar.sync 3, 512;" ::: "memory");
+        s_gofs[bd] = ctl->base[pass][bd] + prev - s_tstart[bd];
+    }
+    // Positions must be final before anybody stages keys: group A knows (its barrier 1), group B
+    // knows (barrier 3); a CTA that is not split simply synchronises.
+    static_assert(!kSplit || WARPS == 16, "a split CTA is exactly groups A and B");
+    if (!kSplit) __syncthreads();
 
     // ---- stage the keys in shared memory in digit order ---------------------------------------------
 #pragma unroll
@@ -364,25 +434,6 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
         const uint32_t d = digit_of(key[i], shift, flip);
         const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
         s_keys[s_table[(warp * kRadixBins + d) * TW + (TW - 1)] + r] = key[i];
-    }
-
-    // ---- decoupled look-back: one thread per digit walks the predecessors' status words ------------
-    if (tid < kRadixBins) {
-        uint32_t prev = 0;
-        if (tile > 0) {
-            const uint32_t *p = status_cur + (size_t)(tile - 1) * kRadixBins + tid;
-            for (;;) {
-                const uint32_t s = ld_relaxed_gpu(p);
-                const uint32_t f = s & ~kValueMask;
-                if (f == 0) continue;               // predecessor has not published yet
-                prev += s & kValueMask;
-                if (f == kFlagIncl) break;
-                p -= kRadixBins;                    // local count only: keep walking back
-            }
-            st_relaxed_gpu(status_cur + (size_t)tile * kRadixBins + tid,
-                           kFlagIncl | ((prev + total) & kValueMask));
-        }
-        s_gofs[tid] = ctl->base[pass][tid] + prev - tile_start;
     }
     __syncthreads();
 
@@ -430,6 +481,33 @@ radix_final_copy_kernel(const int32_t *in_buf, int32_t *out_buf, const int32_t *
     }
 }
 
+// Self-test behind kRankAdd: that mode is stable only if same-address shared-memory atomics issued
+// by one warp instruction are resolved in lane order.  PTX does not promise that; every B200 tried
+// does it (tools/atomic_order_probe.cu).  The library checks it once per process on the device it
+// runs on, with conflict patterns from none to 32-way, and falls back to ballots if it ever fails.
+__global__ void __launch_bounds__(512)
+radix_atomic_order_selftest_kernel(uint32_t *violations)
+{
+    __shared__ uint32_t table[16][kRadixBins];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *t = table[warp];
+    uint32_t x = (blockIdx.x * 512u + threadIdx.x) * 2654435761u + 12345u;
+    uint32_t bad = 0;
+    for (int round = 0; round < 64; ++round) {
+        for (int j = lane; j < kRadixBins; j += 32) t[j] = 0;
+        __syncwarp();
+        x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+        const uint32_t bins = 1u << (round & 7);                 // 1, 2, 4 ... 128 distinct digits
+        const uint32_t d = ((x >> 8) % bins) * ((round & 8) ? 32u : 1u) % kRadixBins;   // also same-bank sets
+        const uint32_t got = atomicAdd(t + d, 1u);
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t want = __popc(peers & lanemask_lt());
+        bad += (got != want);
+        __syncwarp();
+    }
+    if (bad) atomicAdd(violations, bad);
+}
+
 // ================================================================================================
 // host side
 // ================================================================================================
@@ -440,6 +518,7 @@ using OnesweepFn = void (*)(const int32_t *, int32_t *, int32_t *, size_t, int, 
 
 struct Variant {
     const char *name;
+    int mode;
     int threads;
     int tile;
     size_t smem;
@@ -447,27 +526,50 @@ struct Variant {
 };
 
 #define B200_VARIANT(W, I, B, M)                                                                    \
-    { "warps" #W "_ipt" #I "_occ" #B "_" #M, OnesweepShape<W, I, M>::kThreads,                      \
+    { "warps" #W "_ipt" #I "_occ" #B "_" #M, M, OnesweepShape<W, I, M>::kThreads,                      \
       OnesweepShape<W, I, M>::kTile, OnesweepShape<W, I, M>::kSmemBytes,                            \
       radix_onesweep_kernel<W, I, B, M> }
 
 const Variant kVariants[] = {
-    B200_VARIANT(16, 16, 2, kRankBallot),   // 8192-key tiles, 2 CTAs/SM        (default)
-    B200_VARIANT(16, 16, 2, kRankAtomic),
-    B200_VARIANT(16, 16, 2, kRankMatch),
-    B200_VARIANT(8, 24, 3, kRankBallot),    // 6144, fewer threads
-    B200_VARIANT(8, 24, 3, kRankAtomic),
-    B200_VARIANT(16, 20, 2, kRankBallot),   // 10240
-    B200_VARIANT(16, 20, 2, kRankAtomic),
-    B200_VARIANT(8, 16, 4, kRankBallot),    // 4096-key tiles, 4 CTAs/SM
-    B200_VARIANT(8, 16, 4, kRankAtomic),
-    B200_VARIANT(8, 8, 6, kRankBallot),     // 2048 (small-n friendly)
-    B200_VARIANT(12, 16, 3, kRankBallot),   // 6144, 384 threads
-    B200_VARIANT(12, 20, 2, kRankBallot),   // 7680
+    B200_VARIANT(16, 16, 2, kRankAdd),      //  0: 8192-key tiles, 2 CTAs/SM   (default when the self-test passes)
+    B200_VARIANT(16, 18, 2, kRankAdd),      //  1: 9216
+    B200_VARIANT(16, 20, 2, kRankAdd),      //  2: 10240
+    B200_VARIANT(8, 24, 3, kRankAdd),       //  3: 6144, 256 threads
+    B200_VARIANT(8, 16, 4, kRankAdd),       //  4: 4096, 4 CTAs/SM
+    B200_VARIANT(16, 16, 2, kRankBallot),   //  5: the documented-behaviour fallback
+    B200_VARIANT(16, 16, 2, kRankAtomic),   //  6
+    B200_VARIANT(16, 16, 2, kRankMatch),    //  7
+    B200_VARIANT(8, 24, 3, kRankBallot),    //  8
+    B200_VARIANT(8, 8, 6, kRankBallot),     //  9: 2048-key tiles
+    B200_VARIANT(12, 16, 3, kRankAdd),      // 10: 6144, 384 threads
+    B200_VARIANT(16, 12, 2, kRankAdd),      // 11: 6144, 512 threads
 };
+constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 std::atomic<int> g_variant{0};
+std::atomic<int> g_atomic_order{-1};      // -1 unknown, 0 the self-test failed, 1 it passed
+
+int atomic_order_ok() {
+    int v = g_atomic_order.load(std::memory_order_acquire);
+    if (v >= 0) return v;
+    const char *env = getenv("B200SORT_RANK_SAFE");
+    if (env != nullptr && env[0] == '1') { g_atomic_order.store(0); return 0; }
+    uint32_t *d_bad = nullptr, h_bad = 1;
+    if (cudaMalloc(&d_bad, sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaMemset(d_bad, 0, sizeof(uint32_t));
+    radix_atomic_order_selftest_kernel<<<kNumSMs * 2, 512>>>(d_bad);
+    ++g_launch_count;
+    if (cudaMemcpy(&h_bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); h_bad = 1; }
+    cudaFree(d_bad);
+    v = (h_bad == 0) ? 1 : 0;
+    g_atomic_order.store(v, std::memory_order_release);
+    return v;
+}
+
+// The variant to launch: the selected one, unless it needs lane-ordered atomics and this device
+// failed (or was told to skip) the self-test.
+int effective_variant();
 std::atomic<int> g_skip_enabled{1};
 std::atomic<bool> g_attrs_set[kNumVariants];
 
@@ -499,6 +601,15 @@ int hist_grid(size_t n) {
 
 }  // namespace
 
+namespace {
+int effective_variant() {
+    const int v = g_variant.load();
+    if (kVariants[v].mode == kRankAdd && !atomic_order_ok()) return kFallbackVariant;
+    return v;
+}
+}  // namespace
+
+int radix_atomic_order_ok() { return atomic_order_ok(); }
 int radix_num_variants() { return kNumVariants; }
 const char *radix_variant_name(int v) { return (v >= 0 && v < kNumVariants) ? kVariants[v].name : nullptr; }
 int radix_set_variant(int v) {
@@ -508,6 +619,7 @@ int radix_set_variant(int v) {
 }
 void radix_set_skip(int enabled) { g_skip_enabled.store(enabled ? 1 : 0); }
 size_t radix_current_tile() { return (size_t)kVariants[g_variant.load()].tile; }
+const char *radix_effective_variant_name() { return kVariants[effective_variant()].name; }
 
 size_t radix_workspace_bytes(size_t n) {
     const size_t tiles = div_up(n > 0 ? n : 1, kRadixMinTile);
@@ -542,7 +654,7 @@ int radix_single_pass(const int32_t *d_in, int32_t *d_out, size_t n, int pass, v
     if (pass < 0 || pass >= kRadixPasses) return B200SORT_ERR_INVALID;
     if (n == 0) return B200SORT_OK;
     B200_TRY(check_ws(d_ws, ws_bytes, n));
-    const int v = g_variant.load();
+    const int v = effective_variant();
     B200_TRY(ensure_smem_attr(v));
     B200_TRY(ensure_hist_attr());
     const Variant &var = kVariants[v];
@@ -594,7 +706,7 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
         return B200SORT_OK;
     }
     B200_TRY(check_ws(d_ws, ws_bytes, n));
-    const int v = g_variant.load();
+    const int v = effective_variant();
     B200_TRY(ensure_smem_attr(v));
     B200_TRY(ensure_hist_attr());
     const Variant &var = kVariants[v];

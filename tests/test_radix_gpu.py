@@ -175,3 +175,33 @@ def test_out_of_place_form_leaves_the_input_untouched(algo_name):
             torch.cuda.synchronize()
             assert_bit_exact(d_in.cpu().numpy(), keys, f"{dist} n={n}: input modified")
             assert_bit_exact(d_out.cpu().numpy(), oracle.radix_sort(keys), f"{dist} n={n}")
+
+
+def test_safe_rank_fallback_is_selected_by_env_and_sorts():
+    """B200SORT_RANK_SAFE=1 makes the library launch the ballot-ranked shape (documented behaviour
+    only) instead of the atomicAdd-ranked one; the result is the same bytes."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, '.'); sys.path.insert(0, 'tests')\n"
+        "import oracle\n"
+        "from b200sort import datagen\n"
+        "from b200sort._lib import lib, ALGO_RADIX\n"
+        "from helpers import gpu_sort\n"
+        "L = lib()\n"
+        "assert L.b200sort_radix_atomic_order_ok() == 0\n"
+        "assert b'Ballot' in L.b200sort_radix_effective_variant_name()\n"
+        "k = datagen.skewed(300001, 3)\n"
+        "assert gpu_sort(k, ALGO_RADIX).tobytes() == oracle.radix_sort(k).tobytes()\n"
+        "print('ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, "B200SORT_RANK_SAFE": "1"},
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_atomic_order_selftest_reports():
+    assert lib().b200sort_radix_atomic_order_ok() in (0, 1)
+    name = lib().b200sort_radix_effective_variant_name().decode()
+    assert ("kRankAdd" in name) == bool(lib().b200sort_radix_atomic_order_ok())
