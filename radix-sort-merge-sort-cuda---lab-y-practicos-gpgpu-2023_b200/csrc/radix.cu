@@ -17,8 +17,12 @@
 // lane) and keys are loaded warp-striped so that this is memory order.
 #include "radix.cuh"
 
+#include <cooperative_groups.h>
+
 #include <atomic>
 #include <cstdlib>
+
+namespace cg = cooperative_groups;
 
 namespace b200sort {
 
@@ -204,7 +208,7 @@ struct OnesweepShape {
     static constexpr size_t kSmemBytes =
         (size_t)WARPS * kRadixBins * 4 * kTableWords   // per-warp digit counters -> offsets
         + (size_t)kTile * 4                            // keys staged in digit order
-        + (size_t)kRadixBins * 4 * 3                   // global offset, tile total, tile start per digit
+        + (size_t)kRadixBins * 4 * 4                   // global offset, tile total, tile start, chain prefix
         + 64;                                          // warp sums, tile id
 };
 
@@ -213,7 +217,18 @@ __device__ __forceinline__ uint32_t digit_of(int32_t key, int shift, uint32_t fl
     return ((static_cast<uint32_t>(key) >> shift) & (kRadixBins - 1)) ^ flip;
 }
 
-template <int WARPS, int IPT, int MIN_BLOCKS, int MODE>
+// CL > 1: the CTAs of a thread-block cluster take CL consecutive tiles and act as ONE link of the
+// look-back chain: tile totals are exchanged through distributed shared memory, the last CTA of
+// the cluster publishes / looks back for all of them and hands the result to its peers.  The
+// chain then has CL times fewer links, which is what bounds the pass once ranking is cheap.
+__device__ __forceinline__ void cluster_arrive() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int WARPS, int IPT, int MIN_BLOCKS, int MODE, int CL>
 __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
 radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n, int pass,
                       RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
@@ -241,8 +256,8 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     if (follow_plan) {
         if (ctl->skip[pass]) {
             // Identity pass.  Still hand the next pass a clean status buffer.
-            if (status_next != nullptr && tid < kRadixBins)
-                status_next[(size_t)blockIdx.x * kRadixBins + tid] = 0;
+            if (status_next != nullptr && tid < kRadixBins && blockIdx.x % CL == 0)
+                status_next[(size_t)(blockIdx.x / CL) * kRadixBins + tid] = 0;
             return;
         }
         const uint32_t ss = ctl->src_sel[pass], ds = ctl->dst_sel[pass];
@@ -251,16 +266,28 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     }
 
     // Tiles are handed out by ticket so that a tile only ever waits on tiles already running.
-    if (tid == 0) s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
+    uint32_t crank = 0;                                      // my rank inside the cluster
+    if (CL > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        crank = cluster.block_rank();
+        if (crank == 0 && tid == 0) {
+            const uint32_t t = atomicAdd(&ctl->ticket[pass], 1u);
+            for (int q = 0; q < CL; ++q) cluster.map_shared_rank(s_misc, q)[8] = t;
+        }
+    } else {
+        if (tid == 0) s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
+    }
     {
         uint4 *z = reinterpret_cast<uint4 *>(s_table + warp * kRadixBins * TW);
 #pragma unroll
         for (int j = lane; j < kRadixBins * TW / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
     }
-    __syncthreads();
-    const uint32_t tile = s_misc[8];
+    if (CL > 1) { cluster_arrive(); cluster_wait(); } else __syncthreads();
+    const uint32_t link = s_misc[8];                         // my link of the look-back chain
+    const uint32_t tile = link * CL + crank;
     const size_t tile_base = (size_t)tile * kTile;
-    const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
+    const uint32_t valid = (tile_base >= n) ? 0u
+                         : (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
     const int shift = pass * kRadixBits;
     const uint32_t flip = (pass == kRadixPasses - 1) ? 0x80u : 0u;
 
@@ -338,28 +365,31 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     // Named barriers: 1 = inside group A; 2 = "totals are in shared memory" (A arrives, B waits);
     //                 3 = "positions are final" (A arrives, B waits).
     constexpr bool kSplit = (WARPS >= 16);
-    constexpr int kLookWindow = 8;
+    constexpr int kLookWindow = (CL == 1 && IPT <= 16) ? 16 : 8;
     uint32_t *s_total = s_misc + 16;                         // [256]
     uint32_t *s_tstart = s_total + kRadixBins;               // [256]
+    uint32_t *s_prev = s_tstart + kRadixBins;                // [256] (clusters: written by the looker)
 
     const bool in_a = tid < kRadixBins;
     const bool in_b = kSplit ? (tid >= kRadixBins && tid < 2 * kRadixBins) : in_a;
     const uint32_t bd = kSplit ? tid - kRadixBins : tid;     // group B's digit
-    const uint32_t *look = status_cur + (size_t)tile * kRadixBins + bd;   // my digit in my tile's row
+    const uint32_t *look = status_cur + (size_t)link * kRadixBins + bd;   // my digit in my link's row
+    const bool looker = (CL == 1) || (crank == CL - 1);      // the CTA that talks to the chain
 
     uint32_t win[kLookWindow];
-    if (kSplit && in_b) {
+    if (kSplit && in_b && looker) {
         // first window, issued before anything else so that it overlaps group A's work
 #pragma unroll
         for (int j = 0; j < kLookWindow; ++j)
-            win[j] = (tile >= (uint32_t)(j + 1)) ? ld_relaxed_gpu(look - (size_t)(j + 1) * kRadixBins)
-                                                 : kFlagIncl;            // before tile 0: inclusive 0
+            win[j] = (link >= (uint32_t)(j + 1)) ? ld_relaxed_gpu(look - (size_t)(j + 1) * kRadixBins)
+                                                 : kFlagIncl;            // before link 0: inclusive 0
     }
     if (in_a) {
         uint32_t total = 0;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) total += s_table[(w * kRadixBins + tid) * TW + (TW - 1)];
         s_total[tid] = total;
+        if (CL > 1) cluster_arrive();                        // #1: my totals are in shared memory
         if (kSplit) { __threadfence_block(); asm volatile("bar.arrive 2, 512;" ::: "memory"); }
         uint32_t x = total;
 #pragma unroll
@@ -384,48 +414,80 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
         s_tstart[tid] = tile_start;
         if (kSplit) { __threadfence_block(); asm volatile("bar.arrive 3, 512;" ::: "memory"); }
         asm volatile("bar.sync 1, 256;" ::: "memory");      // every (warp, digit) position is final
+        if (CL > 1) { cluster_wait(); cluster_arrive(); }    // finish #1; #2: nothing to announce
     }
+    if (CL > 1 && !in_a && !in_b) { cluster_arrive(); cluster_wait(); cluster_arrive(); }
     if (in_b) {
         if (kSplit) asm volatile("bar.sync 2, 512;" ::: "memory");
-        const uint32_t total = s_total[bd];
-        st_relaxed_gpu(const_cast<uint32_t *>(look), (tile == 0 ? kFlagIncl : kFlagLocal) | total);
-        if (status_next != nullptr) status_next[(size_t)tile * kRadixBins + bd] = 0;
-        uint32_t prev = 0;
-        if (tile > 0) {
-            uint32_t back = 1;                               // distance of the window's first tile
-            bool have = kSplit;                              // window already loaded?
-            for (;;) {
-                if (!have) {
+        uint32_t total = s_total[bd];                        // my tile; becomes my link's total
+        uint32_t before = 0;                                 // same digit in earlier tiles of my link
+        if (CL > 1) {
+            if (kSplit) cluster_arrive();                    // #1 (group A arrived for itself)
+            cluster_wait();                                  // every CTA's totals are readable
+            cg::cluster_group cluster = cg::this_cluster();
+            uint32_t rest = 0;
 #pragma unroll
-                    for (int j = 0; j < kLookWindow; ++j)
-                        win[j] = (tile >= back + j) ? ld_relaxed_gpu(look - (size_t)(back + j) * kRadixBins)
-                                                    : kFlagIncl;
+            for (int q = 0; q < CL; ++q) {
+                if (looker ? (q < CL - 1) : (q < (int)crank)) {
+                    const uint32_t c = cluster.map_shared_rank(s_total, q)[bd];
+                    if (q < (int)crank) before += c;
+                    rest += c;
                 }
-                have = false;
-                bool done = false;
-                uint32_t used = 0;
+            }
+            if (looker) total += rest;
+        }
+        uint32_t prev = 0;
+        if (looker) {
+            st_relaxed_gpu(const_cast<uint32_t *>(look), (link == 0 ? kFlagIncl : kFlagLocal) | total);
+            if (status_next != nullptr) status_next[(size_t)link * kRadixBins + bd] = 0;
+            if (link > 0) {
+                uint32_t back = 1;                           // distance of the window's first link
+                bool have = kSplit;                          // window already loaded?
+                for (;;) {
+                    if (!have) {
 #pragma unroll
-                for (int j = 0; j < kLookWindow; ++j) {
-                    if (!done && used == (uint32_t)j) {
-                        const uint32_t f = win[j] & ~kValueMask;
-                        if (f != 0) {                        // published: take it
-                            prev += win[j] & kValueMask;
-                            used = j + 1;
-                            done = (f == kFlagIncl);
+                        for (int j = 0; j < kLookWindow; ++j)
+                            win[j] = (link >= back + j) ? ld_relaxed_gpu(look - (size_t)(back + j) * kRadixBins)
+                                                        : kFlagIncl;
+                    }
+                    have = false;
+                    bool done = false;
+                    uint32_t used = 0;
+#pragma unroll
+                    for (int j = 0; j < kLookWindow; ++j) {
+                        if (!done && used == (uint32_t)j) {
+                            const uint32_t f = win[j] & ~kValueMask;
+                            if (f != 0) {                    // published: take it
+                                prev += win[j] & kValueMask;
+                                used = j + 1;
+                                done = (f == kFlagIncl);
+                            }
                         }
                     }
+                    if (done) break;
+                    back += used;                            // re-poll from the first unpublished link
                 }
-                if (done) break;
-                back += used;                                // re-poll from the first unpublished tile
+                st_relaxed_gpu(const_cast<uint32_t *>(look), kFlagIncl | ((prev + total) & kValueMask));
             }
-            st_relaxed_gpu(const_cast<uint32_t *>(look), kFlagIncl | ((prev + total) & kValueMask));
+            if (CL > 1) {                                    // hand the chain prefix to my peers
+                cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+                for (int q = 0; q < CL - 1; ++q) cluster.map_shared_rank(s_prev, q)[bd] = prev;
+            }
+        }
+        __syncwarp();                                        // the look-back loop diverges per digit
+        if (CL > 1) {
+            cluster_arrive();                                // #2: the prefix is in everybody's memory
+            cluster_wait();
+            if (!looker) prev = s_prev[bd];
         }
         if (kSplit) asm volatile("bar.sync 3, 512;" ::: "memory");
-        s_gofs[bd] = ctl->base[pass][bd] + prev - s_tstart[bd];
+        s_gofs[bd] = ctl->base[pass][bd] + prev + before - s_tstart[bd];
     }
     // Positions must be final before anybody stages keys: group A knows (its barrier 1), group B
     // knows (barrier 3); a CTA that is not split simply synchronises.
     static_assert(!kSplit || WARPS == 16, "a split CTA is exactly groups A and B");
+    static_assert(CL == 1 || kSplit, "clustered shapes use the split layout");
     if (!kSplit) __syncthreads();
 
     // ---- stage the keys in shared memory in digit order ---------------------------------------------
@@ -435,6 +497,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
         const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
         s_keys[s_table[(warp * kRadixBins + d) * TW + (TW - 1)] + r] = key[i];
     }
+    if (CL > 1 && !in_b) cluster_wait();                     // finish #2 (group B already did)
     __syncthreads();
 
     // ---- scatter: consecutive threads write consecutive addresses inside each digit run -----------
@@ -519,30 +582,38 @@ using OnesweepFn = void (*)(const int32_t *, int32_t *, int32_t *, size_t, int, 
 struct Variant {
     const char *name;
     int mode;
+    int cluster;
     int threads;
     int tile;
     size_t smem;
     OnesweepFn fn;
 };
 
-#define B200_VARIANT(W, I, B, M)                                                                    \
-    { "warps" #W "_ipt" #I "_occ" #B "_" #M, M, OnesweepShape<W, I, M>::kThreads,                      \
+#define B200_VARIANT(W, I, B, M, C)                                                                 \
+    { "warps" #W "_ipt" #I "_occ" #B "_" #M "_cl" #C, M, C, OnesweepShape<W, I, M>::kThreads,         \
       OnesweepShape<W, I, M>::kTile, OnesweepShape<W, I, M>::kSmemBytes,                            \
-      radix_onesweep_kernel<W, I, B, M> }
+      radix_onesweep_kernel<W, I, B, M, C> }
 
 const Variant kVariants[] = {
-    B200_VARIANT(16, 16, 2, kRankAdd),      //  0: 8192-key tiles, 2 CTAs/SM   (default when the self-test passes)
-    B200_VARIANT(16, 18, 2, kRankAdd),      //  1: 9216
-    B200_VARIANT(16, 20, 2, kRankAdd),      //  2: 10240
-    B200_VARIANT(8, 24, 3, kRankAdd),       //  3: 6144, 256 threads
-    B200_VARIANT(8, 16, 4, kRankAdd),       //  4: 4096, 4 CTAs/SM
-    B200_VARIANT(16, 16, 2, kRankBallot),   //  5: the documented-behaviour fallback
-    B200_VARIANT(16, 16, 2, kRankAtomic),   //  6
-    B200_VARIANT(16, 16, 2, kRankMatch),    //  7
-    B200_VARIANT(8, 24, 3, kRankBallot),    //  8
-    B200_VARIANT(8, 8, 6, kRankBallot),     //  9: 2048-key tiles
-    B200_VARIANT(12, 16, 3, kRankAdd),      // 10: 6144, 384 threads
-    B200_VARIANT(16, 12, 2, kRankAdd),      // 11: 6144, 512 threads
+    B200_VARIANT(16, 16, 2, kRankAdd, 1),      //  0: 8192-key tiles, 2 CTAs/SM
+    B200_VARIANT(16, 18, 2, kRankAdd, 1),      //  1: 9216
+    B200_VARIANT(16, 20, 2, kRankAdd, 1),      //  2: 10240
+    B200_VARIANT(8, 24, 3, kRankAdd, 1),       //  3: 6144, 256 threads
+    B200_VARIANT(8, 16, 4, kRankAdd, 1),       //  4: 4096, 4 CTAs/SM
+    B200_VARIANT(16, 16, 2, kRankBallot, 1),   //  5: the documented-behaviour fallback
+    B200_VARIANT(16, 16, 2, kRankAtomic, 1),   //  6
+    B200_VARIANT(16, 16, 2, kRankMatch, 1),    //  7
+    B200_VARIANT(8, 24, 3, kRankBallot, 1),    //  8
+    B200_VARIANT(8, 8, 6, kRankBallot, 1),     //  9: 2048-key tiles
+    B200_VARIANT(12, 16, 3, kRankAdd, 1),      // 10: 6144, 384 threads
+    B200_VARIANT(16, 12, 2, kRankAdd, 1),      // 11: 6144, 512 threads
+    B200_VARIANT(16, 16, 2, kRankAdd, 2),      // 12: clusters of 2 / 4 / 8 CTAs = one chain link
+    B200_VARIANT(16, 16, 2, kRankAdd, 4),      // 13
+    B200_VARIANT(16, 16, 2, kRankAdd, 8),      // 14
+    B200_VARIANT(16, 18, 2, kRankAdd, 4),      // 15
+    B200_VARIANT(16, 20, 2, kRankAdd, 4),      // 16
+    B200_VARIANT(16, 20, 2, kRankAdd, 8),      // 17
+    B200_VARIANT(16, 16, 2, kRankBallot, 4),   // 18
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
@@ -590,6 +661,31 @@ int ensure_hist_attr() {
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHistSmemBytes));
         g_hist_attr_set.store(true, std::memory_order_release);
     }
+    return B200SORT_OK;
+}
+
+int launch_onesweep(const Variant &var, size_t tiles, cudaStream_t s, const int32_t *in, int32_t *out,
+                    int32_t *tmp, size_t n, int pass, RadixControl *ctl, uint32_t *cur, uint32_t *next,
+                    int follow_plan) {
+    const unsigned grid = (unsigned)(div_up(tiles, (size_t)var.cluster) * var.cluster);
+    if (var.cluster == 1) {
+        var.fn<<<grid, var.threads, var.smem, s>>>(in, out, tmp, n, pass, ctl, cur, next, follow_plan);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid, 1, 1);
+        cfg.blockDim = dim3((unsigned)var.threads, 1, 1);
+        cfg.dynamicSmemBytes = var.smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = (unsigned)var.cluster;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, var.fn, in, out, tmp, n, pass, ctl, cur, next, follow_plan));
+    }
+    B200_LAUNCH_CHECK();
     return B200SORT_OK;
 }
 
@@ -665,9 +761,7 @@ int radix_single_pass(const int32_t *d_in, int32_t *d_out, size_t n, int pass, v
     radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_in, n, ctl, status0,
                                                                  tiles * kRadixBins, 0, 0);
     B200_LAUNCH_CHECK();
-    var.fn<<<(unsigned)tiles, var.threads, var.smem, s>>>(d_in, d_out, nullptr, n, pass, ctl, status0,
-                                                          nullptr, 0);
-    B200_LAUNCH_CHECK();
+    B200_TRY(launch_onesweep(var, tiles, s, d_in, d_out, nullptr, n, pass, ctl, status0, nullptr, 0));
     return B200SORT_OK;
 }
 
@@ -728,8 +822,7 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
     for (int pass = 0; pass < kRadixPasses; ++pass) {
         uint32_t *cur = status[pass & 1];
         uint32_t *next = (pass + 1 < kRadixPasses) ? status[(pass + 1) & 1] : nullptr;
-        var.fn<<<(unsigned)tiles, var.threads, var.smem, s>>>(d_in, d_out, d_tmp, n, pass, ctl, cur, next, 1);
-        B200_LAUNCH_CHECK();
+        B200_TRY(launch_onesweep(var, tiles, s, d_in, d_out, d_tmp, n, pass, ctl, cur, next, 1));
         B200_TRY(timer.mark());
     }
     if (skip) {
