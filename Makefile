@@ -15,7 +15,7 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -W
 REFROOT ?= /root/reference
 SRM     := $(REFROOT)/Sord Radix y Merge
 
-SRCS := $(CSRC)/radix.cu $(CSRC)/merge.cu $(CSRC)/api.cu $(CSRC)/lab_shim.cu
+SRCS := $(CSRC)/radix.cu $(CSRC)/merge.cu $(CSRC)/dist.cu $(CSRC)/api.cu $(CSRC)/lab_shim.cu
 HDRS := $(wildcard $(CSRC)/*.cuh) include/b200sort.h include/lab.h include/utils.h
 OBJS := $(patsubst $(CSRC)/%.cu,build/obj/%.o,$(SRCS))
 LIB  := $(PKG)/libb200sort.so

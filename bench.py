@@ -358,6 +358,8 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-log2n", type=int, default=27, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange: fused peer-write scatter (default) or NCCL all-to-all")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

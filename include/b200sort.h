@@ -147,6 +147,51 @@ void b200sort_host_release(void);
 int  b200sort_host_alloc_pinned(void **h_ptr, size_t bytes);
 int  b200sort_host_free_pinned(void *h_ptr);
 
+/* ---- one-box multi-GPU sort (one process per GPU; collectives are the caller's plumbing) -------
+ * No reference counterpart (north_star (c)).
+ * Phase 1  b200sort_dist_histogram_i32   local 2^bits-bin histogram of the top bits of key^0x80000000
+ * (caller) all-gather (all-reduce) of the counts over NCCL
+ * Phase 2  b200sort_dist_plan            pure host function: contiguous bin ranges -> ranks
+ * Phase 3  b200sort_dist_partition_i32   multisplit of the local keys into per-destination blocks;
+ *                                        the destination table may hold local pointers (then an
+ *                                        NCCL all-to-all moves the blocks) or peer-mapped pointers
+ *                                        (then the scatter IS the exchange, over NVLink)
+ * Phase 4  b200sort_sort_copy_i32        local sort of what arrived */
+#define B200SORT_DIST_BITS_MIN 4
+#define B200SORT_DIST_BITS_MAX 12
+#define B200SORT_DIST_MAX_WORLD 16
+/* d_hist: uint64[2^bits], overwritten. */
+int b200sort_dist_histogram_i32(const int32_t *d_keys, size_t n, int bits,
+                                unsigned long long *d_hist, void *stream);
+/* Host planner (no device work).  all_hist[r*nbins + b] = rank r's count of bin b, nbins = 2^bits.
+ * Outputs (each may be NULL except bin_owner):
+ *   bin_owner[b]   in [0, world), non-decreasing in b: every rank owns one contiguous value range,
+ *                  balanced to about total/world keys;
+ *   recv_count[r]  keys rank r will own after the exchange;
+ *   send_count[r]  keys THIS rank (`rank`) sends to rank r;
+ *   dst_offset[r]  element offset inside rank r's receive buffer at which this rank's block
+ *                  starts (receive buffers are laid out source rank by source rank). */
+int b200sort_dist_plan(const unsigned long long *all_hist, int world, int rank, int bits,
+                       int *bin_owner, unsigned long long *recv_count,
+                       unsigned long long *send_count, unsigned long long *dst_offset);
+/* h_dst_base[r]  (HOST array of `world` device-visible pointers) base of rank r's receive buffer;
+ * d_bin_owner    device copy of the planner's bin_owner (int[2^bits]);
+ * h_dst_offset   HOST array, the planner's dst_offset;
+ * d_ws           b200sort_dist_workspace_bytes(n, bits) bytes, 256-byte aligned. */
+size_t b200sort_dist_workspace_bytes(size_t n, int bits);
+int b200sort_dist_partition_i32(const int32_t *d_keys, size_t n, int bits, int world,
+                                int32_t *const *h_dst_base, const int *d_bin_owner,
+                                const unsigned long long *h_dst_offset,
+                                void *d_ws, size_t ws_bytes, void *stream);
+/* Plain cudaMalloc / cudaFree (receive buffers must be whole allocations to be exported) and the
+ * CUDA IPC plumbing that lets ranks (separate processes) map each other's receive buffers. */
+#define B200SORT_IPC_HANDLE_BYTES 64
+int b200sort_device_malloc(void **d_ptr, size_t bytes);
+int b200sort_device_free(void *d_ptr);
+int b200sort_ipc_export(void *d_ptr, unsigned char *handle /* [B200SORT_IPC_HANDLE_BYTES] */);
+int b200sort_ipc_open(const unsigned char *handle, void **d_ptr);
+int b200sort_ipc_close(void *d_ptr);
+
 #ifdef __cplusplus
 }
 #endif

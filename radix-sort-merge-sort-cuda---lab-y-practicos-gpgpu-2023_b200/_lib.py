@@ -55,6 +55,15 @@ SIGNATURES = {
     "b200sort_radix_effective_variant_name": (ctypes.c_char_p, []),
     "b200sort_launch_count": (_u64, []),
     "b200sort_launch_count_reset": (None, []),
+    "b200sort_dist_histogram_i32": (_i, [_vp, _sz, _i, _vp, _vp]),
+    "b200sort_dist_plan": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "b200sort_dist_workspace_bytes": (_sz, [_sz, _i]),
+    "b200sort_dist_partition_i32": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200sort_device_malloc": (_i, [ctypes.POINTER(_vp), _sz]),
+    "b200sort_device_free": (_i, [_vp]),
+    "b200sort_ipc_export": (_i, [_vp, _vp]),
+    "b200sort_ipc_open": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "b200sort_ipc_close": (_i, [_vp]),
     "b200sort_order_array_host": (_i, [_vp, _sz, _i]),
     "b200sort_order_with_trust_host": (_i, [_vp, _sz]),
     "b200sort_host_release": (None, []),

@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" surface of libb200sort.so (include/b200sort.h) and the host-array
 // operator that stands where the lab's order_array stood (SRM/lab.cu:303-402).
 #include "common.cuh"
+#include "dist.cuh"
 #include "merge.cuh"
 #include "radix.cuh"
 
@@ -307,6 +308,59 @@ int b200sort_host_alloc_pinned(void **h_ptr, size_t bytes) {
 }
 int b200sort_host_free_pinned(void *h_ptr) {
     B200_CUDA_TRY(cudaFreeHost(h_ptr));
+    return B200SORT_OK;
+}
+
+
+// ---- one-box multi-GPU path -------------------------------------------------------------------------
+int b200sort_dist_histogram_i32(const int32_t *d_keys, size_t n, int bits, unsigned long long *d_hist,
+                                void *stream) {
+    if (d_hist == nullptr || (n > 0 && d_keys == nullptr) || n > B200SORT_MAX_N) return B200SORT_ERR_INVALID;
+    if (bits < B200SORT_DIST_BITS_MIN) return B200SORT_ERR_INVALID;
+    return dist_histogram(d_keys, n, bits, d_hist, static_cast<cudaStream_t>(stream));
+}
+int b200sort_dist_plan(const unsigned long long *all_hist, int world, int rank, int bits, int *bin_owner,
+                       unsigned long long *recv_count, unsigned long long *send_count,
+                       unsigned long long *dst_offset) {
+    if (bits < B200SORT_DIST_BITS_MIN) return B200SORT_ERR_INVALID;
+    return dist_plan(all_hist, world, rank, bits, bin_owner, recv_count, send_count, dst_offset);
+}
+size_t b200sort_dist_workspace_bytes(size_t n, int bits) { return dist_workspace_bytes(n, bits); }
+int b200sort_dist_partition_i32(const int32_t *d_keys, size_t n, int bits, int world,
+                                int32_t *const *h_dst_base, const int *d_bin_owner,
+                                const unsigned long long *h_dst_offset, void *d_ws, size_t ws_bytes,
+                                void *stream) {
+    if ((n > 0 && d_keys == nullptr) || n > B200SORT_MAX_N || bits < B200SORT_DIST_BITS_MIN)
+        return B200SORT_ERR_INVALID;
+    return dist_partition(d_keys, n, bits, world, h_dst_base, d_bin_owner, h_dst_offset, d_ws, ws_bytes,
+                          static_cast<cudaStream_t>(stream));
+}
+int b200sort_device_malloc(void **d_ptr, size_t bytes) {
+    if (d_ptr == nullptr) return B200SORT_ERR_INVALID;
+    B200_CUDA_TRY(cudaMalloc(d_ptr, bytes));
+    return B200SORT_OK;
+}
+int b200sort_device_free(void *d_ptr) {
+    B200_CUDA_TRY(cudaFree(d_ptr));
+    return B200SORT_OK;
+}
+int b200sort_ipc_export(void *d_ptr, unsigned char *handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200SORT_IPC_HANDLE_BYTES, "handle size");
+    if (d_ptr == nullptr || handle == nullptr) return B200SORT_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    B200_CUDA_TRY(cudaIpcGetMemHandle(&h, d_ptr));
+    std::memcpy(handle, &h, sizeof h);
+    return B200SORT_OK;
+}
+int b200sort_ipc_open(const unsigned char *handle, void **d_ptr) {
+    if (d_ptr == nullptr || handle == nullptr) return B200SORT_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    B200_CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200SORT_OK;
+}
+int b200sort_ipc_close(void *d_ptr) {
+    B200_CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
     return B200SORT_OK;
 }
 

@@ -1,0 +1,238 @@
+// dist.cu -- one-box multi-GPU sort: the device kernels and the host planner (north_star (c)).
+//
+// No reference counterpart (the lab is single-GPU, SRM/run.sh:11).  One process per GPU; the
+// collectives (counts all-gather / all-reduce, optional NCCL all-to-all) are the caller's
+// plumbing (torch.distributed in <pkg>/dist.py).  This file provides
+//
+//   dist_histogram_kernel   2^bits-bin histogram of the top `bits` bits of key ^ 0x80000000
+//                           (the MSD-digit partition histogram).                    4 B/key
+//   dist_plan               pure host function: contiguous bin ranges -> ranks, balanced on the
+//                           global counts; per-rank send / receive counts and the offset of this
+//                           rank's block inside every destination's receive buffer.
+//   dist_partition_kernel   multisplit of the local keys by destination rank, staged through
+//                           shared memory so that every destination receives coalesced runs.
+//                           The destination table holds device-visible base pointers: local
+//                           pointers (then an NCCL all-to-all moves the blocks) or peer-mapped
+//                           pointers (then the scatter IS the exchange: the stores travel over
+//                           NVLink while the kernel is still partitioning).   4 B/key read + 4 B/key
+//                           written (locally or on the peers).
+//
+// The order of keys inside a destination block is irrelevant (a full local sort follows), so the
+// multisplit is unstable and ranks keys with plain shared-memory atomicAdd.
+#include "dist.cuh"
+
+#include <cstring>
+#include <vector>
+
+namespace b200sort {
+
+constexpr int kDistThreads = 512;
+constexpr int kDistIpt = 16;
+constexpr int kDistTile = kDistThreads * kDistIpt;     // 8192 keys per tile
+constexpr int kDistMaxWorld = 16;
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDistThreads)
+dist_histogram_kernel(const int32_t *__restrict__ keys, size_t n, int bits, unsigned long long *hist)
+{
+    extern __shared__ uint32_t sh[];                   // 2^bits counters
+    const uint32_t nbins = 1u << bits;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < nbins; i += kDistThreads) sh[i] = 0;
+    __syncthreads();
+    const int shift = 32 - bits;
+
+    size_t head = ((16 - (reinterpret_cast<uintptr_t>(keys) & 15)) & 15) / 4;
+    if (head > n) head = n;
+    const size_t nvec = (n - head) / 4;
+    const size_t tail_start = head + nvec * 4;
+    const int4 *v = reinterpret_cast<const int4 *>(keys + head);
+    // a block handles at most 2^32 / (its share) keys; counters are 32-bit and n <= 2^30
+    for (size_t i = (size_t)blockIdx.x * kDistThreads + tid; i < nvec; i += (size_t)gridDim.x * kDistThreads) {
+        const int4 r = ld_stream_v4(v + i);
+        atomicAdd(&sh[key_bits(r.x) >> shift], 1u);
+        atomicAdd(&sh[key_bits(r.y) >> shift], 1u);
+        atomicAdd(&sh[key_bits(r.z) >> shift], 1u);
+        atomicAdd(&sh[key_bits(r.w) >> shift], 1u);
+    }
+    if (blockIdx.x == 0) {
+        for (size_t i = tid; i < head; i += kDistThreads) atomicAdd(&sh[key_bits(keys[i]) >> shift], 1u);
+        for (size_t i = tail_start + tid; i < n; i += kDistThreads) atomicAdd(&sh[key_bits(keys[i]) >> shift], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < nbins; i += kDistThreads)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct DistPartitionArgs {
+    int32_t *dst_base[kDistMaxWorld];                  // receive buffer of every rank
+    unsigned long long dst_offset[kDistMaxWorld];      // where this rank's block starts in it
+};
+
+__global__ void __launch_bounds__(kDistThreads, 2)
+dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int world,
+                      const int *__restrict__ bin_owner, DistPartitionArgs args,
+                      unsigned long long *cursor /* [world], zeroed */)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t *s_keys = reinterpret_cast<int32_t *>(smem_raw);                  // [kDistTile]
+    uint8_t *s_dest = reinterpret_cast<uint8_t *>(s_keys + kDistTile);        // [kDistTile]
+    uint8_t *s_owner = s_dest + kDistTile;                                    // [2^bits]
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_owner + (1u << bits));   // [kDistMaxWorld]
+    uint32_t *s_start = s_cnt + kDistMaxWorld;                                // [kDistMaxWorld + 1]
+    unsigned long long *s_gbase = reinterpret_cast<unsigned long long *>(s_start + kDistMaxWorld + 2);
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nbins = 1u << bits;
+    const int shift = 32 - bits;
+    for (uint32_t i = tid; i < nbins; i += kDistThreads) s_owner[i] = (uint8_t)bin_owner[i];
+
+    const size_t tiles = (n + kDistTile - 1) / kDistTile;
+    for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const size_t base = tile * kDistTile;
+        const uint32_t valid = (n - base < (size_t)kDistTile) ? (uint32_t)(n - base) : (uint32_t)kDistTile;
+        if (tid < kDistMaxWorld) s_cnt[tid] = 0;
+        __syncthreads();                               // also: s_owner ready, previous tile drained
+
+        int32_t key[kDistIpt];
+        uint32_t slot[kDistIpt];                       // (dest << 16) | rank inside the tile's dest group
+#pragma unroll
+        for (int i = 0; i < kDistIpt; ++i) {
+            const uint32_t p = i * kDistThreads + tid;
+            if (p < valid) key[i] = ld_stream(keys + base + p);
+        }
+#pragma unroll
+        for (int i = 0; i < kDistIpt; ++i) {
+            const uint32_t p = i * kDistThreads + tid;
+            if (p < valid) {
+                const uint32_t d = s_owner[key_bits(key[i]) >> shift];
+                slot[i] = (d << 16) | atomicAdd(&s_cnt[d], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t run = 0;
+            for (int d = 0; d < world; ++d) { s_start[d] = run; run += s_cnt[d]; }
+            s_start[world] = run;
+        }
+        if (tid < (uint32_t)world && s_cnt[tid] > 0)   // reserve this tile's share of every destination
+            s_gbase[tid] = args.dst_offset[tid] + atomicAdd(&cursor[tid], (unsigned long long)s_cnt[tid]);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kDistIpt; ++i) {
+            const uint32_t p = i * kDistThreads + tid;
+            if (p < valid) {
+                const uint32_t d = slot[i] >> 16;
+                const uint32_t q = s_start[d] + (slot[i] & 0xffffu);
+                s_keys[q] = key[i];
+                s_dest[q] = (uint8_t)d;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kDistIpt; ++i) {
+            const uint32_t q = i * kDistThreads + tid;
+            if (q < valid) {
+                const uint32_t d = s_dest[q];
+                st_stream(args.dst_base[d] + s_gbase[d] + (q - s_start[d]), s_keys[q]);
+            }
+        }
+    }
+}
+
+// ================================================================================================
+size_t dist_workspace_bytes(size_t, int) { return 256; }    // the destination cursors
+
+static size_t partition_smem(int bits) {
+    return (size_t)kDistTile * 4 + kDistTile + ((size_t)1 << bits) + (kDistMaxWorld * 2 + 2) * 4
+           + kDistMaxWorld * 8 + 16;
+}
+
+int dist_histogram(const int32_t *d_keys, size_t n, int bits, unsigned long long *d_hist, cudaStream_t s) {
+    if (bits < B200SORT_DIST_BITS_MIN || bits > B200SORT_DIST_BITS_MAX) return B200SORT_ERR_INVALID;
+    const size_t nbins = (size_t)1 << bits;
+    B200_CUDA_TRY(cudaMemsetAsync(d_hist, 0, nbins * sizeof(unsigned long long), s));
+    if (n == 0) return B200SORT_OK;
+    const size_t want = div_up(div_up(n, 4), (size_t)kDistThreads * 4);
+    const unsigned grid = (unsigned)(want < (size_t)kNumSMs * 3 ? (want ? want : 1) : (size_t)kNumSMs * 3);
+    dist_histogram_kernel<<<grid, kDistThreads, nbins * sizeof(uint32_t), s>>>(d_keys, n, bits, d_hist);
+    B200_LAUNCH_CHECK();
+    return B200SORT_OK;
+}
+
+int dist_plan(const unsigned long long *all_hist, int world, int rank, int bits, int *bin_owner,
+              unsigned long long *recv_count, unsigned long long *send_count,
+              unsigned long long *dst_offset) {
+    if (all_hist == nullptr || bin_owner == nullptr || world < 1 || world > kDistMaxWorld || rank < 0 ||
+        rank >= world || bits < 1 || bits > B200SORT_DIST_BITS_MAX)
+        return B200SORT_ERR_INVALID;
+    const size_t nbins = (size_t)1 << bits;
+    std::vector<unsigned long long> global(nbins, 0);
+    unsigned long long total = 0;
+    for (int r = 0; r < world; ++r)
+        for (size_t b = 0; b < nbins; ++b) { global[b] += all_hist[(size_t)r * nbins + b]; }
+    for (size_t b = 0; b < nbins; ++b) total += global[b];
+
+    // Contiguous bin ranges: rank r ends at the bin boundary closest to (r+1)/world of the keys.
+    // Owners are non-decreasing in the bin index, so the concatenation of the ranks' sorted
+    // outputs is globally sorted and signed order is kept (bins index key ^ 0x80000000).
+    unsigned long long cum = 0;
+    int owner = 0;
+    for (size_t b = 0; b < nbins; ++b) {
+        while (owner < world - 1) {
+            // keys that ranks 0..owner should hold together
+            const long double target = (long double)total * (owner + 1) / world;
+            // give bin b to the next rank if starting it here leaves `owner` closer to its target
+            if ((long double)cum >= target ||
+                ((long double)cum + (long double)global[b] / 2 > target && cum > 0 &&
+                 (long double)cum + (long double)global[b] > target))
+                ++owner;
+            else
+                break;
+        }
+        bin_owner[b] = owner;
+        cum += global[b];
+    }
+    if (recv_count) std::memset(recv_count, 0, sizeof(unsigned long long) * world);
+    if (send_count) std::memset(send_count, 0, sizeof(unsigned long long) * world);
+    if (dst_offset) std::memset(dst_offset, 0, sizeof(unsigned long long) * world);
+    for (size_t b = 0; b < nbins; ++b) {
+        const int o = bin_owner[b];
+        if (recv_count) recv_count[o] += global[b];
+        if (send_count) send_count[o] += all_hist[(size_t)rank * nbins + b];
+        if (dst_offset)
+            for (int s = 0; s < rank; ++s) dst_offset[o] += all_hist[(size_t)s * nbins + b];
+    }
+    return B200SORT_OK;
+}
+
+int dist_partition(const int32_t *d_keys, size_t n, int bits, int world, int32_t *const *h_dst_base,
+                   const int *d_bin_owner, const unsigned long long *h_dst_offset, void *d_ws,
+                   size_t ws_bytes, cudaStream_t s) {
+    if (bits < B200SORT_DIST_BITS_MIN || bits > B200SORT_DIST_BITS_MAX || world < 1 || world > kDistMaxWorld ||
+        h_dst_base == nullptr || h_dst_offset == nullptr || d_bin_owner == nullptr)
+        return B200SORT_ERR_INVALID;
+    if (d_ws == nullptr || ws_bytes < dist_workspace_bytes(n, bits)) return B200SORT_ERR_WORKSPACE;
+    if (n == 0) return B200SORT_OK;
+    DistPartitionArgs args;
+    std::memset(&args, 0, sizeof args);
+    for (int r = 0; r < world; ++r) { args.dst_base[r] = h_dst_base[r]; args.dst_offset[r] = h_dst_offset[r]; }
+    static thread_local bool attr_set = false;
+    const size_t smem = partition_smem(bits);
+    if (!attr_set) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)partition_smem(B200SORT_DIST_BITS_MAX)));
+        attr_set = true;
+    }
+    auto *cursor = static_cast<unsigned long long *>(d_ws);
+    B200_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long) * kDistMaxWorld, s));
+    const size_t tiles = div_up(n, kDistTile);
+    const unsigned grid = (unsigned)(tiles < (size_t)kNumSMs * 2 ? tiles : (size_t)kNumSMs * 2);
+    dist_partition_kernel<<<grid, kDistThreads, smem, s>>>(d_keys, n, bits, world, d_bin_owner, args, cursor);
+    B200_LAUNCH_CHECK();
+    return B200SORT_OK;
+}
+
+}  // namespace b200sort

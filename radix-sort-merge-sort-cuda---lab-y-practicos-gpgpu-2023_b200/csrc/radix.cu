@@ -377,6 +377,8 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     const bool looker = (CL == 1) || (crank == CL - 1);      // the CTA that talks to the chain
 
     uint32_t win[kLookWindow];
+    uint32_t digit_base = 0;                                 // global start of my digit (group B)
+    if (in_b) digit_base = ctl->base[pass][bd];              // fetched early: it is off the critical path
     if (kSplit && in_b && looker) {
         // first window, issued before anything else so that it overlaps group A's work
 #pragma unroll
@@ -482,7 +484,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             if (!looker) prev = s_prev[bd];
         }
         if (kSplit) asm volatile("bar.sync 3, 512;" ::: "memory");
-        s_gofs[bd] = ctl->base[pass][bd] + prev + before - s_tstart[bd];
+        s_gofs[bd] = digit_base + prev + before - s_tstart[bd];
     }
     // Positions must be final before anybody stages keys: group A knows (its barrier 1), group B
     // knows (barrier 3); a CTA that is not split simply synchronises.
@@ -595,9 +597,9 @@ struct Variant {
       radix_onesweep_kernel<W, I, B, M, C> }
 
 const Variant kVariants[] = {
-    B200_VARIANT(16, 16, 2, kRankAdd, 1),      //  0: 8192-key tiles, 2 CTAs/SM
+    B200_VARIANT(16, 20, 2, kRankAdd, 1),      //  0: 10240-key tiles, 2 CTAs/SM  (default; fastest measured)
     B200_VARIANT(16, 18, 2, kRankAdd, 1),      //  1: 9216
-    B200_VARIANT(16, 20, 2, kRankAdd, 1),      //  2: 10240
+    B200_VARIANT(16, 16, 2, kRankAdd, 1),      //  2: 8192
     B200_VARIANT(8, 24, 3, kRankAdd, 1),       //  3: 6144, 256 threads
     B200_VARIANT(8, 16, 4, kRankAdd, 1),       //  4: 4096, 4 CTAs/SM
     B200_VARIANT(16, 16, 2, kRankBallot, 1),   //  5: the documented-behaviour fallback

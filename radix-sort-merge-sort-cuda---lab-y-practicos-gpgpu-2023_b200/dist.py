@@ -1,0 +1,308 @@
+"""One-box multi-GPU sort: MSD partition + exchange over NVLink + local radix sort.
+
+One process per GPU (``torchrun``); ``torch.distributed`` is the plumbing (NCCL on GPUs, gloo in
+the CPU tests).  No reference counterpart: the lab is single-GPU (SRM/run.sh:11); this is
+north_star (c) / SURVEY.md section 8(e).
+
+    phase 1  every rank histograms the top ``bits`` bits of its keys      (CUDA, b200sort_dist_histogram_i32)
+    phase 2  counts are all-gathered (their sum is the all-reduce north_star names); a pure host
+             planner gives each rank one contiguous value range of ~total/world keys
+                                                                          (C, b200sort_dist_plan)
+    phase 3  every rank multisplits its keys by destination              (CUDA, b200sort_dist_partition_i32)
+               exchange="p2p"   the destination table holds the peers' receive buffers (CUDA IPC
+                                mapped): the kernel's coalesced stores ARE the exchange and cross
+                                NVLink while partitioning continues  -- the fused path, default;
+               exchange="nccl"  the kernel fills a local send buffer and an NCCL all-to-all moves
+                                the blocks -- the baseline the fused path is measured against;
+    phase 4  every rank radix-sorts what it received                       (CUDA, b200sort_sort_copy_i32)
+
+Rank r ends up holding the r-th contiguous slice of the global order (sizes differ by the
+granularity of the 2^bits bins); concatenating the ranks' outputs gives the sorted array.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+import time
+
+import numpy as np
+
+from ._lib import ALGO_RADIX, check, lib
+
+DEFAULT_BITS = 12
+
+
+# ---- host-side pieces (also exercised on CPU by the gloo tests) ------------------------------------
+
+def plan(all_hist: np.ndarray, rank: int, bits: int):
+    """b200sort_dist_plan: (bin_owner int32[nbins], recv_count, send_count, dst_offset uint64[world])."""
+    all_hist = np.ascontiguousarray(all_hist, dtype=np.uint64)
+    world, nbins = all_hist.shape
+    assert nbins == 1 << bits
+    owner = np.zeros(nbins, dtype=np.int32)
+    recv = np.zeros(world, dtype=np.uint64)
+    send = np.zeros(world, dtype=np.uint64)
+    offs = np.zeros(world, dtype=np.uint64)
+    check(lib().b200sort_dist_plan(all_hist.ctypes.data, world, rank, bits, owner.ctypes.data,
+                                   recv.ctypes.data, send.ctypes.data, offs.ctypes.data))
+    return owner, recv, send, offs
+
+
+def host_histogram(keys: np.ndarray, bits: int) -> np.ndarray:
+    """numpy twin of b200sort_dist_histogram_i32 (CPU tests of the host logic only)."""
+    top = (keys.view(np.uint32) ^ np.uint32(0x80000000)) >> np.uint32(32 - bits)
+    return np.bincount(top.astype(np.int64), minlength=1 << bits).astype(np.uint64)
+
+
+# ---- the GPU path ---------------------------------------------------------------------------------------
+
+class DistSorter:
+    """Owns this rank's receive / scratch / output buffers and the peer mappings."""
+
+    def __init__(self, n_local: int, bits: int = DEFAULT_BITS, exchange: str = "p2p", headroom: float = 1.25,
+                 group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.bits, self.nbins = bits, 1 << bits
+        self.exchange = exchange
+        self.n_local = int(n_local)
+        self.cap = int(self.n_local * headroom) + 4096
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        L = lib()
+        check(L.b200sort_device_check())
+        # receive buffer: a whole cudaMalloc allocation so that it can be exported over CUDA IPC
+        p = ctypes.c_void_p()
+        check(L.b200sort_device_malloc(ctypes.byref(p), self.cap * 4))
+        self.recv_ptr = p.value
+        self.tmp = torch.empty(self.cap, dtype=torch.int32, device=self.dev)
+        self.out = torch.empty(self.cap, dtype=torch.int32, device=self.dev)
+        self.hist = torch.zeros(self.nbins, dtype=torch.int64, device=self.dev)
+        self.all_hist = torch.zeros(self.world * self.nbins, dtype=torch.int64, device=self.dev)
+        self.owner_dev = torch.zeros(self.nbins, dtype=torch.int32, device=self.dev)
+        ws = max(L.b200sort_workspace_bytes(self.cap, ALGO_RADIX), L.b200sort_dist_workspace_bytes(self.cap, bits))
+        self.ws = torch.empty(ws + 512, dtype=torch.uint8, device=self.dev)
+        self.ws_ptr = self.ws.data_ptr() + (-self.ws.data_ptr()) % 256
+        self.ws_bytes = ws
+        self.part_ws = torch.zeros(512, dtype=torch.uint8, device=self.dev)
+        self.part_ws_ptr = self.part_ws.data_ptr() + (-self.part_ws.data_ptr()) % 256
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.peer_ptrs = [None] * self.world
+        self.send = None
+        if exchange == "p2p":
+            handle = (ctypes.c_ubyte * 64)()
+            check(L.b200sort_ipc_export(self.recv_ptr, handle))
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.dev)
+            everyone = [torch.zeros(64, dtype=torch.uint8, device=self.dev) for _ in range(self.world)]
+            dist.all_gather(everyone, mine, group=group)
+            for r in range(self.world):
+                if r == self.rank:
+                    self.peer_ptrs[r] = self.recv_ptr
+                else:
+                    h = (ctypes.c_ubyte * 64)(*everyone[r].cpu().tolist())
+                    q = ctypes.c_void_p()
+                    check(L.b200sort_ipc_open(h, ctypes.byref(q)))
+                    self.peer_ptrs[r] = q.value
+        elif exchange == "nccl":
+            self.send = torch.empty(self.n_local, dtype=torch.int32, device=self.dev)
+            self.recv_t = torch.empty(self.cap, dtype=torch.int32, device=self.dev)
+        else:
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.last = {}
+
+    def close(self) -> None:
+        L = lib()
+        self.torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)
+        for r, p in enumerate(self.peer_ptrs):
+            if p is not None and r != self.rank:
+                L.b200sort_ipc_close(p)
+        self.peer_ptrs = [None] * self.world
+        self.dist.barrier(group=self.group)
+        if self.recv_ptr:
+            L.b200sort_device_free(self.recv_ptr)
+            self.recv_ptr = None
+
+    def sort(self, keys):
+        """Sort the distributed array whose local part is the int32 CUDA tensor ``keys`` (read
+        only).  Returns (tensor view of this rank's slice of the global order, its length)."""
+        torch, dist, L = self.torch, self.dist, lib()
+        n = keys.numel()
+        assert n <= self.n_local and keys.dtype == torch.int32 and keys.is_cuda and keys.is_contiguous()
+        stream = torch.cuda.current_stream().cuda_stream
+        # phase 1
+        check(L.b200sort_dist_histogram_i32(keys.data_ptr(), n, self.bits, self.hist.data_ptr(), stream))
+        # phase 2: counts of every rank (world x nbins, 8 B each: latency-bound); the host planner
+        # needs them, so this is the one host synchronisation of the sort
+        dist.all_gather_into_tensor(self.all_hist, self.hist, group=self.group)
+        all_hist = self.all_hist.cpu().numpy().astype(np.uint64).reshape(self.world, self.nbins)
+        owner, recv, send, offs = plan(all_hist, self.rank, self.bits)
+        m = int(recv[self.rank])
+        if int(recv.max()) > self.cap:
+            raise RuntimeError(f"rank would receive {int(recv.max())} keys, receive buffers hold {self.cap}: "
+                               "raise headroom (skewed keys)")
+        self.owner_dev.copy_(torch.from_numpy(owner), non_blocking=False)
+        # phase 3
+        if self.exchange == "p2p":
+            base = (ctypes.c_void_p * self.world)(*self.peer_ptrs)
+            offs_c = offs
+        else:
+            send_disp = np.concatenate([[0], np.cumsum(send)[:-1]]).astype(np.uint64)
+            base = (ctypes.c_void_p * self.world)(*([self.send.data_ptr()] * self.world))
+            offs_c = send_disp
+        check(L.b200sort_dist_partition_i32(keys.data_ptr(), n, self.bits, self.world, base,
+                                            self.owner_dev.data_ptr(), offs_c.ctypes.data,
+                                            self.part_ws_ptr, 256, stream))
+        if self.exchange == "p2p":
+            # stream-ordered barrier: nobody sorts before every peer's stores have landed
+            dist.all_reduce(self.flag, group=self.group)
+            recv_ptr = self.recv_ptr
+        else:
+            in_splits = [int(all_hist[s][owner == self.rank].sum()) for s in range(self.world)]
+            out_splits = [int(x) for x in send]
+            dist.all_to_all_single(self.recv_t[:m], self.send[:n], in_splits, out_splits, group=self.group)
+            recv_ptr = self.recv_t.data_ptr()
+        # phase 4
+        check(L.b200sort_sort_copy_i32(ALGO_RADIX, recv_ptr, self.out.data_ptr(), self.tmp.data_ptr(), m,
+                                       self.ws_ptr, self.ws_bytes, stream))
+        self.last = {"recv": m, "sent_remote": int(send.sum() - send[self.rank]), "recv_counts": recv}
+        return self.out[:m], m
+
+
+# ---- bench.py --gpus N -----------------------------------------------------------------------------------
+
+def bench_main(args, metric: str, unit: str, ClockSampler, peaks_fn) -> None:
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if rank == 0:
+            print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})"}))
+        return
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n_local = 1 << args.log2n
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    if args.dist == "uniform":
+        src = torch.randint(-2**31, 2**31, (n_local,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+    elif args.dist == "skewed90":
+        src = torch.randint(-2**31, 2**31, (n_local,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+        hot = torch.rand(n_local, device=dev, generator=g) < 0.9
+        src = torch.where(hot, (src & 0x00FFFFFF) | 0x40000000, src)
+    else:
+        raise SystemExit("multi-GPU bench supports --dist uniform|skewed90")
+    sorter = DistSorter(n_local, exchange=args.exchange, headroom=1.25 if args.dist == "uniform" else float(world))
+    L = lib()
+
+    def global_check(out, m):
+        ok = bool((out[1:] >= out[:-1]).all().item()) if m > 1 else True
+        lo = out[0].item() if m > 0 else 2**31 - 1
+        hi = out[m - 1].item() if m > 0 else -2**31
+        edges = torch.tensor([lo, hi, m, int(out.sum(dtype=torch.int64).item()) if m else 0], dtype=torch.int64, device=dev)
+        allv = [torch.zeros_like(edges) for _ in range(world)]
+        dist.all_gather(allv, edges)
+        tot_in = torch.tensor([int(src.sum(dtype=torch.int64).item())], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot_in)
+        prev_hi = -2**31
+        for e in allv:
+            if int(e[2]) > 0:
+                assert int(e[0]) >= prev_hi, "bench: rank boundaries out of order"
+                prev_hi = int(e[1])
+        assert ok, "bench: a rank's slice is not sorted"
+        assert sum(int(e[2]) for e in allv) == world * n_local, "bench: key count changed"
+        assert sum(int(e[3]) for e in allv) == int(tot_in.item()), "bench: multiset sum changed"
+
+    for _ in range(max(args.warmup, 3)):
+        out, m = sorter.sort(src)
+    torch.cuda.synchronize()
+    global_check(out, m)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.02)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    L.b200sort_launch_count_reset()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        out, m = sorter.sort(src)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t1 = time.perf_counter()
+    launches = int(L.b200sort_launch_count())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_per_step = ms_total / args.steps
+    global_check(out, m)
+    total_keys = world * n_local
+
+    sent = sorter.last.get("sent_remote", 0)
+
+    # e2e: host buffers in, host buffers out (pinned), every step
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h_in = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+    h_in.copy_(src)
+    h_out = torch.empty(sorter.cap, dtype=torch.int32, pin_memory=True)
+    d_in = torch.empty_like(src)
+    torch.cuda.synchronize()
+    dist.barrier()
+    el = 0.0
+    for i in range(e2e_steps + 1):
+        dist.barrier()
+        t = time.perf_counter()
+        d_in.copy_(h_in, non_blocking=True)
+        o, mm = sorter.sort(d_in)
+        h_out[:mm].copy_(o, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if i > 0:
+            el += float(dt.item())
+    e2e_value = total_keys * e2e_steps / el
+
+    recv_all = [int(x) for x in sorter.last["recv_counts"]]
+    if rank == 0:
+        peaks = peaks_fn()
+        per_gpu_bytes = 40.0 * n_local      # hist 4 + partition 8 + local sort 36 - (first hist shared) ~ 48; see DESIGN.md
+        line = {
+            "metric": metric, "value": total_keys / (ms_per_step / 1e3), "unit": unit, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": f"distributed radix sort, n=2^{args.log2n} {args.dist} int32 keys PER GPU "
+                                   f"({world} x 2^{args.log2n} = {total_keys} keys), MSD partition on the top "
+                                   f"{sorter.bits} bits + exchange + local onesweep",
+                       "exchange": "fused peer-write scatter over NVLink (CUDA IPC mapped receive buffers)"
+                                   if args.exchange == "p2p" else "NCCL all_to_all_single",
+                       "dist": args.dist, "seed": "1000+rank", "n_per_gpu": n_local,
+                       "l2": "inputs larger than L2", "recv_counts": recv_all},
+            "roofline": {"bound": "hbm", "achieved": 48.0 * n_local / (ms_per_step / 1e3) / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": 48.0 * n_local / (ms_per_step / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "kernel": "whole distributed sort per GPU: 4 (MSD histogram) + 8 (partition/exchange) + "
+                                   "36 (local sort) = 48 B/key of HBM traffic",
+                         "peak_source": peaks["source"],
+                         "nvlink_bytes_sent_per_gpu": 4 * sent},
+            "cpu_baseline": None,
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": 4 * n_local * world,
+                    "d2h_bytes_per_step": 4 * n_local * world, "steps": e2e_steps,
+                    "api": "DistSorter.sort on pinned host buffers: H2D + distributed sort + D2H per rank"},
+            "gpu_launches": launches * world, "clocks": sampler.summary(t0, t1),
+        }
+        print(json.dumps(line), flush=True)
+    sorter.close()
+    dist.destroy_process_group()
