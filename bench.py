@@ -37,6 +37,21 @@ METRIC = "32-bit keys sorted/sec at n=2^28"
 UNIT = "keys/s"
 
 
+def _ncu_traffic(kernel_substr: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full summary
+    (profiles/rNN_ncu_*.json, written by tools/ncu_summary.py), or None."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*.json"))):
+        try:
+            for item in json.load(open(path)):
+                if kernel_substr in item.get("kernel", "") and "dram_bytes_total" in item:
+                    best = {"bytes": item["dram_bytes_total"], "source": os.path.relpath(path, ROOT)}
+        except Exception:
+            pass
+    return best
+
+
 def _peaks() -> dict:
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -283,8 +298,11 @@ def ours_single(args) -> None:
         dominant = "merge_pass_kernel (+ its partition kernel; one merge pass: 8 B/key)"
         algo_bytes_total = 8.0 * n * (1 + passes)
     achieved = bytes_per_launch / (kernel_ms / 1e3) / 1e9
+    traffic = _ncu_traffic("radix_onesweep" if algo == ALGO_RADIX else "merge_pass") if args.log2n == 28 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": dominant,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic["bytes"] if traffic else None,
+                "traffic_source": traffic["source"] if traffic else None,
+                "algorithmic_bytes": bytes_per_launch, "kernel": dominant,
                 "kernel_ms": kernel_ms, "peak_source": peaks["source"],
                 "whole_sort_gbs": algo_bytes_total / (ms_per_step / 1e3) / 1e9,
                 "whole_sort_frac": algo_bytes_total / (ms_per_step / 1e3) / 1e9 / peaks["hbm_gbs"],
