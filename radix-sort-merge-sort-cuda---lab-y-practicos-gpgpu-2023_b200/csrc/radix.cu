@@ -522,6 +522,293 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     }
 }
 
+// ================================================================================================
+// k2': the same pass as a PERSISTENT, software-pipelined CTA
+// ================================================================================================
+// One CTA per SM slot loops over tiles (tickets).  14 worker warps load / rank / stage / write the
+// keys; 2 chain warps own everything that talks to other tiles (publish the tile's digit counts,
+// decoupled look-back with 128-bit status loads, publish the inclusive counts, global offsets).
+// The workers never wait for the chain on the tile they are ranking: tile i is written out only
+// after tile i+1 has been ranked and staged (double-buffered staging area), and the global loads
+// of tile i+1 are in flight while tile i-1 is being written.  So neither the look-back latency
+// nor the load latency sits on the workers' critical path.
+constexpr int kPPWorkerWarps = 14;
+constexpr int kPPWorkers = kPPWorkerWarps * 32;      // 448
+constexpr int kPPThreads = 512;
+constexpr int kPPChain = kPPThreads - kPPWorkers;    // 64 threads, 4 digits each
+constexpr uint32_t kPPPoison = 0xFFFFFFFFu;
+enum { kBarW = 1, kBarA = 2, kBarTotals = 3, kBarTstart = 5, kBarGofs = 7 };   // +buffer for the last three
+
+__device__ __forceinline__ void bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const uint32_t *p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_v4(uint32_t *p, uint4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int IPT>
+struct PipelinedShape {
+    static constexpr int kTile = kPPWorkers * IPT;
+    static constexpr size_t kSmemBytes =
+        (size_t)kPPWorkerWarps * kRadixBins * 4     // per-warp digit counters -> positions
+        + (size_t)2 * kTile * 4                     // two staging buffers
+        + (size_t)3 * 2 * kRadixBins * 4            // gofs, total, tstart, double-buffered
+        + 128;                                      // warp sums, tickets, tile ids
+};
+
+template <int IPT>
+__global__ void __launch_bounds__(kPPThreads, 2)
+radix_onesweep_pipelined_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
+                                int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
+                                int follow_plan)
+{
+    constexpr int kTile = PipelinedShape<IPT>::kTile;
+    static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in pairs");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *s_table  = reinterpret_cast<uint32_t *>(smem_raw);                     // [14][256]
+    int32_t  *s_keys   = reinterpret_cast<int32_t *>(s_table + kPPWorkerWarps * kRadixBins);   // [2][kTile]
+    uint32_t *s_gofs   = reinterpret_cast<uint32_t *>(s_keys + 2 * kTile);           // [2][256]
+    uint32_t *s_total  = s_gofs + 2 * kRadixBins;                                    // [2][256]
+    uint32_t *s_tstart = s_total + 2 * kRadixBins;                                   // [2][256]
+    uint32_t *s_misc   = s_tstart + 2 * kRadixBins;     // [0..7] warp sums, [8..9] next ticket, [10..11] tile id
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t tiles = (n + kTile - 1) / kTile;
+
+    const int32_t *in = in_buf;
+    int32_t *out = out_buf;
+    if (follow_plan) {
+        if (ctl->skip[pass]) {
+            if (status_next != nullptr)
+                for (size_t row = blockIdx.x; row < tiles; row += gridDim.x)
+                    if (tid < kRadixBins) status_next[row * kRadixBins + tid] = 0;
+            return;
+        }
+        const uint32_t ss = ctl->src_sel[pass], ds = ctl->dst_sel[pass];
+        in = (ss == kSelIn) ? in_buf : (ss == kSelTmp) ? tmp_buf : out_buf;
+        out = (ds == kSelTmp) ? tmp_buf : out_buf;
+    }
+    const int shift = pass * kRadixBits;
+    const uint32_t flip = (pass == kRadixPasses - 1) ? 0x80u : 0u;
+
+    if (warp >= kPPWorkerWarps) {
+        // ======================== chain warps ========================
+        const uint32_t c4 = (tid - kPPWorkers) * 4;                 // my four digits
+        const uint4 base4 = *reinterpret_cast<const uint4 *>(&ctl->base[pass][c4]);
+        int b = 0;
+        for (;;) {
+            bar_sync(kBarTotals + b, kRadixBins + kPPChain);
+            const uint32_t tile = s_misc[10 + b];
+            if (tile == kPPPoison) break;
+            const uint4 tot = *reinterpret_cast<const uint4 *>(s_total + b * kRadixBins + c4);
+            uint32_t *row = status_cur + (size_t)tile * kRadixBins + c4;
+            const uint32_t flag0 = (tile == 0) ? kFlagIncl : kFlagLocal;
+            st_relaxed_gpu_v4(row, make_uint4(flag0 | tot.x, flag0 | tot.y, flag0 | tot.z, flag0 | tot.w));
+            if (status_next != nullptr)
+                *reinterpret_cast<uint4 *>(status_next + (size_t)tile * kRadixBins + c4) = make_uint4(0, 0, 0, 0);
+            uint32_t prev[4] = {0, 0, 0, 0};
+            if (tile > 0) {
+                constexpr int W = 4;
+                uint32_t need[4] = {1, 1, 1, 1};        // distance of the next status word to take
+                bool done[4] = {false, false, false, false};
+                uint32_t back = 1;
+                for (;;) {
+                    uint4 win[W];
+#pragma unroll
+                    for (int j = 0; j < W; ++j)
+                        win[j] = (tile >= back + j) ? ld_relaxed_gpu_v4(row - (size_t)(back + j) * kRadixBins)
+                                                    : make_uint4(kFlagIncl, kFlagIncl, kFlagIncl, kFlagIncl);
+#pragma unroll
+                    for (int j = 0; j < W; ++j) {
+                        const uint32_t w4[4] = {win[j].x, win[j].y, win[j].z, win[j].w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (!done[k] && need[k] == back + j) {
+                                const uint32_t f = w4[k] & ~kValueMask;
+                                if (f != 0) {
+                                    prev[k] += w4[k] & kValueMask;
+                                    need[k] += 1;
+                                    done[k] = (f == kFlagIncl);
+                                }
+                            }
+                        }
+                    }
+                    if (done[0] && done[1] && done[2] && done[3]) break;
+                    uint32_t nb = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (!done[k] && need[k] < nb) nb = need[k];
+                    back = nb;
+                }
+                st_relaxed_gpu_v4(row, make_uint4(kFlagIncl | ((prev[0] + tot.x) & kValueMask),
+                                                  kFlagIncl | ((prev[1] + tot.y) & kValueMask),
+                                                  kFlagIncl | ((prev[2] + tot.z) & kValueMask),
+                                                  kFlagIncl | ((prev[3] + tot.w) & kValueMask)));
+            }
+            __syncwarp();
+            bar_sync(kBarTstart + b, kRadixBins + kPPChain);
+            const uint4 ts = *reinterpret_cast<const uint4 *>(s_tstart + b * kRadixBins + c4);
+            *reinterpret_cast<uint4 *>(s_gofs + b * kRadixBins + c4) =
+                make_uint4(base4.x + prev[0] - ts.x, base4.y + prev[1] - ts.y,
+                           base4.z + prev[2] - ts.z, base4.w + prev[3] - ts.w);
+            __threadfence_block();
+            bar_arrive(kBarGofs + b, kPPThreads);
+            b ^= 1;
+        }
+        return;
+    }
+
+    // ============================ worker warps ============================
+    uint32_t *wt = s_table + warp * kRadixBins;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(wt);
+#pragma unroll
+        for (int j = lane; j < kRadixBins / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
+    bar_sync(kBarW, kPPWorkers);
+    uint32_t tile = s_misc[8];
+    uint32_t prev_tile = kPPPoison;
+    const uint32_t wofs = warp * (32 * IPT) + lane;
+
+    int32_t key[IPT];
+    auto load_tile = [&](uint32_t t) {
+        const size_t tile_base = (size_t)t * kTile;
+        const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
+        const int32_t *src = in + tile_base + wofs;
+        if (valid == (uint32_t)kTile) {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) key[i] = ld_stream(src + i * 32);
+        } else {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i)
+                key[i] = (wofs + i * 32 < valid) ? ld_stream(src + i * 32) : 0x7FFFFFFF;
+        }
+    };
+    auto write_tile = [&](uint32_t t, int buf) {
+        const size_t tile_base = (size_t)t * kTile;
+        const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
+        const int32_t *sk = s_keys + buf * kTile;
+        const uint32_t *go = s_gofs + buf * kRadixBins;
+        if (valid == (uint32_t)kTile) {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const uint32_t p = tid + j * kPPWorkers;
+                const int32_t k = sk[p];
+                st_stream(out + (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p), k);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const uint32_t p = tid + j * kPPWorkers;
+                if (p < valid) {
+                    const int32_t k = sk[p];
+                    st_stream(out + (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p), k);
+                }
+            }
+        }
+    };
+
+    if (tile < tiles) load_tile(tile);
+    int b = 0;
+    uint32_t iter = 0;
+    while (tile < tiles) {
+        // ---- rank: one shared-memory atomicAdd per key (lane-ordered; see the self-test) ----------
+        uint32_t rank2[IPT / 2];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint32_t r = atomicAdd(wt + digit_of(key[i], shift, flip), 1u);
+            rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
+        }
+        bar_sync(kBarW, kPPWorkers);
+        // next ticket (everybody has read the slot being overwritten: that read precedes this barrier)
+        if (tid == 0) s_misc[8 + ((iter + 1) & 1)] = atomicAdd(&ctl->ticket[pass], 1u);
+
+        // ---- threads 0..255, thread = digit: totals -> chain; scan; counts -> positions ----------
+        if (tid < kRadixBins) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < kPPWorkerWarps; ++w) total += s_table[w * kRadixBins + tid];
+            s_total[b * kRadixBins + tid] = total;
+            if (tid == 0) s_misc[10 + b] = tile;
+            __threadfence_block();
+            bar_arrive(kBarTotals + b, kRadixBins + kPPChain);
+            uint32_t x = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= (uint32_t)o) x += y;
+            }
+            if (lane == 31) s_misc[warp] = x;
+            bar_sync(kBarA, kRadixBins);
+            uint32_t add = 0;
+#pragma unroll
+            for (int w = 0; w < kRadixBins / 32; ++w) add += (w < (int)warp) ? s_misc[w] : 0u;
+            const uint32_t tile_start = x - total + add;
+            uint32_t run = tile_start;
+#pragma unroll
+            for (int w = 0; w < kPPWorkerWarps; ++w) {
+                const uint32_t c = s_table[w * kRadixBins + tid];
+                s_table[w * kRadixBins + tid] = run;
+                run += c;
+            }
+            s_tstart[b * kRadixBins + tid] = tile_start;
+            __threadfence_block();
+            bar_arrive(kBarTstart + b, kRadixBins + kPPChain);
+        }
+        bar_sync(kBarW, kPPWorkers);                       // positions are final
+        const uint32_t next = s_misc[8 + ((iter + 1) & 1)];
+
+        // ---- stage this tile's keys in digit order ----------------------------------------------------
+        {
+            int32_t *sk = s_keys + b * kTile;
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
+                sk[wt[digit_of(key[i], shift, flip)] + r] = key[i];
+            }
+        }
+        __syncwarp();
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(wt);      // my warp's counters, for the next tile
+#pragma unroll
+            for (int j = lane; j < kRadixBins / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+
+        // ---- loads of the next tile go out now and land while the previous tile is written ----
+        if (next < tiles) load_tile(next);
+        if (prev_tile != kPPPoison) {
+            bar_sync(kBarGofs + (b ^ 1), kPPThreads);      // the chain finished tile i-1 long ago
+            write_tile(prev_tile, b ^ 1);
+        }
+        prev_tile = tile;
+        tile = next;
+        b ^= 1;
+        ++iter;
+    }
+    if (prev_tile != kPPPoison) {
+        bar_sync(kBarW, kPPWorkers);                       // the last tile is fully staged
+        bar_sync(kBarGofs + (b ^ 1), kPPThreads);
+        write_tile(prev_tile, b ^ 1);
+    }
+    if (tid < kRadixBins) {                                // release the chain warps
+        if (tid == 0) s_misc[10 + b] = kPPPoison;
+        __threadfence_block();
+        bar_arrive(kBarTotals + b, kRadixBins + kPPChain);
+    }
+}
+
 // The plan's final copy (only ever needed with pass skipping): tmp -> out when an in-place sort
 // executed an odd number of passes, in -> out when an out-of-place sort executed none.
 __global__ void __launch_bounds__(256)
@@ -584,7 +871,7 @@ using OnesweepFn = void (*)(const int32_t *, int32_t *, int32_t *, size_t, int, 
 struct Variant {
     const char *name;
     int mode;
-    int cluster;
+    int cluster;       // CTAs per cluster (1 = none); 0 marks the persistent pipelined kernel
     int threads;
     int tile;
     size_t smem;
@@ -595,6 +882,10 @@ struct Variant {
     { "warps" #W "_ipt" #I "_occ" #B "_" #M "_cl" #C, M, C, OnesweepShape<W, I, M>::kThreads,         \
       OnesweepShape<W, I, M>::kTile, OnesweepShape<W, I, M>::kSmemBytes,                            \
       radix_onesweep_kernel<W, I, B, M, C> }
+
+#define B200_PP_VARIANT(I)                                                                          \
+    { "pipelined_14w_ipt" #I "_kRankAdd", kRankAdd, 0, kPPThreads, PipelinedShape<I>::kTile,        \
+      PipelinedShape<I>::kSmemBytes, radix_onesweep_pipelined_kernel<I> }
 
 const Variant kVariants[] = {
     B200_VARIANT(16, 20, 2, kRankAdd, 1),      //  0: 10240-key tiles, 2 CTAs/SM  (default; fastest measured)
@@ -616,6 +907,10 @@ const Variant kVariants[] = {
     B200_VARIANT(16, 20, 2, kRankAdd, 4),      // 16
     B200_VARIANT(16, 20, 2, kRankAdd, 8),      // 17
     B200_VARIANT(16, 16, 2, kRankBallot, 4),   // 18
+    B200_PP_VARIANT(20),                       // 19: persistent pipelined, 448 x 20 = 8960-key tiles
+    B200_PP_VARIANT(16),                       // 20: 7168
+    B200_PP_VARIANT(24),                       // 21: 10752
+    B200_PP_VARIANT(18),                       // 22: 8064
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
@@ -669,6 +964,13 @@ int ensure_hist_attr() {
 int launch_onesweep(const Variant &var, size_t tiles, cudaStream_t s, const int32_t *in, int32_t *out,
                     int32_t *tmp, size_t n, int pass, RadixControl *ctl, uint32_t *cur, uint32_t *next,
                     int follow_plan) {
+    if (var.cluster == 0) {          // persistent: one CTA per resident slot, tiles by ticket
+        const unsigned slots = 2u * kNumSMs;
+        const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
+        var.fn<<<grid, var.threads, var.smem, s>>>(in, out, tmp, n, pass, ctl, cur, next, follow_plan);
+        B200_LAUNCH_CHECK();
+        return B200SORT_OK;
+    }
     const unsigned grid = (unsigned)(div_up(tiles, (size_t)var.cluster) * var.cluster);
     if (var.cluster == 1) {
         var.fn<<<grid, var.threads, var.smem, s>>>(in, out, tmp, n, pass, ctl, cur, next, follow_plan);
