@@ -537,6 +537,7 @@ constexpr int kPPWorkers = kPPWorkerWarps * 32;      // 448
 constexpr int kPPThreads = 512;
 constexpr int kPPChain = kPPThreads - kPPWorkers;    // 64 threads, 4 digits each
 constexpr uint32_t kPPPoison = 0xFFFFFFFFu;
+constexpr int kPPWindow = 8;                         // status rows in flight per chain thread
 enum { kBarW = 1, kBarA = 2, kBarTotals = 3, kBarTstart = 5, kBarGofs = 7 };   // +buffer for the last three
 
 __device__ __forceinline__ void bar_sync(int id, int count) {
@@ -554,6 +555,53 @@ __device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const uint32_t *p) {
 __device__ __forceinline__ void st_relaxed_gpu_v4(uint32_t *p, uint4 v) {
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Two-level look-back.  Tiles are grouped kPPGroup at a time.  A tile's prefix is
+//   (sum of the totals of the earlier GROUPS) + (sum of the totals of the earlier tiles of ITS group).
+// Both sums are walks over status rows whose partial values do not depend on any other walk (a
+// tile's own total, a group's own total), so no tile waits for a long serial chain: the inclusive
+// front only has to advance one GROUP per round trip.  (With one level the front must advance one
+// tile per round trip times the window, which is what bounded the pass: ~35 tiles start per
+// microsecond and a status round trip through L2 takes ~0.4 us.)
+constexpr int kPPGroup = 32;
+
+// Walk back over status rows: row at distance d (1 <= d <= max_dist) is `first - (d-1)*256`; each
+// thread handles four digits with 128-bit loads, W rows in flight.  Flags: 0 not published yet
+// (poll again), kFlagLocal partial (keep walking), kFlagIncl inclusive (stop).  Rows beyond
+// max_dist count as inclusive zero.  acc[k] += everything taken.
+template <int W>
+__device__ __forceinline__ void chain_walk(const uint32_t *first, uint32_t max_dist, uint32_t (&acc)[4]) {
+    uint32_t need[4] = {1, 1, 1, 1};
+    bool done[4] = {false, false, false, false};
+    uint32_t back = 1;
+    for (;;) {
+        uint4 win[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            win[j] = (back + j <= max_dist) ? ld_relaxed_gpu_v4(first - (size_t)(back + j - 1) * kRadixBins)
+                                            : make_uint4(kFlagIncl, kFlagIncl, kFlagIncl, kFlagIncl);
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const uint32_t w4[4] = {win[j].x, win[j].y, win[j].z, win[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!done[k] && need[k] == back + j) {
+                    const uint32_t f = w4[k] & ~kValueMask;
+                    if (f != 0) {
+                        acc[k] += w4[k] & kValueMask;
+                        need[k] += 1;
+                        done[k] = (f == kFlagIncl);
+                    }
+                }
+            }
+        }
+        if (done[0] && done[1] && done[2] && done[3]) break;
+        uint32_t nb = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (!done[k] && need[k] < nb) nb = need[k];
+        back = nb;
+    }
 }
 
 template <int IPT>
@@ -590,8 +638,9 @@ radix_onesweep_pipelined_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t
     int32_t *out = out_buf;
     if (follow_plan) {
         if (ctl->skip[pass]) {
+            const size_t rows = tiles + (tiles + kPPGroup - 1) / kPPGroup;       // tile rows + group rows
             if (status_next != nullptr)
-                for (size_t row = blockIdx.x; row < tiles; row += gridDim.x)
+                for (size_t row = blockIdx.x; row < rows; row += gridDim.x)
                     if (tid < kRadixBins) status_next[row * kRadixBins + tid] = 0;
             return;
         }
@@ -612,48 +661,39 @@ radix_onesweep_pipelined_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t
             const uint32_t tile = s_misc[10 + b];
             if (tile == kPPPoison) break;
             const uint4 tot = *reinterpret_cast<const uint4 *>(s_total + b * kRadixBins + c4);
-            uint32_t *row = status_cur + (size_t)tile * kRadixBins + c4;
-            const uint32_t flag0 = (tile == 0) ? kFlagIncl : kFlagLocal;
+            const uint32_t group = tile / kPPGroup, r = tile % kPPGroup;
+            const bool last_of_group = (r == kPPGroup - 1) || ((size_t)tile + 1 == tiles);
+            uint32_t *row = status_cur + (size_t)tile * kRadixBins + c4;                 // tile rows
+            uint32_t *grow = status_cur + (tiles + group) * kRadixBins + c4;             // group rows follow
+            const uint32_t flag0 = (r == 0) ? kFlagIncl : kFlagLocal;                    // inclusive WITHIN the group
             st_relaxed_gpu_v4(row, make_uint4(flag0 | tot.x, flag0 | tot.y, flag0 | tot.z, flag0 | tot.w));
-            if (status_next != nullptr)
+            if (status_next != nullptr) {
                 *reinterpret_cast<uint4 *>(status_next + (size_t)tile * kRadixBins + c4) = make_uint4(0, 0, 0, 0);
+                if (last_of_group)
+                    *reinterpret_cast<uint4 *>(status_next + (tiles + group) * kRadixBins + c4) = make_uint4(0, 0, 0, 0);
+            }
+            // level 1: earlier tiles of my group
             uint32_t prev[4] = {0, 0, 0, 0};
-            if (tile > 0) {
-                constexpr int W = 4;
-                uint32_t need[4] = {1, 1, 1, 1};        // distance of the next status word to take
-                bool done[4] = {false, false, false, false};
-                uint32_t back = 1;
-                for (;;) {
-                    uint4 win[W];
+            if (r > 0) {
+                chain_walk<kPPWindow>(row - kRadixBins, r, prev);
+                st_relaxed_gpu_v4(row, make_uint4(kFlagIncl | (prev[0] + tot.x), kFlagIncl | (prev[1] + tot.y),
+                                                  kFlagIncl | (prev[2] + tot.z), kFlagIncl | (prev[3] + tot.w)));
+            }
+            // level 2: earlier groups (the last tile of a group owns the group's row)
+            const uint32_t gflag = (group == 0) ? kFlagIncl : kFlagLocal;
+            const uint4 gtot = make_uint4(prev[0] + tot.x, prev[1] + tot.y, prev[2] + tot.z, prev[3] + tot.w);
+            if (last_of_group)
+                st_relaxed_gpu_v4(grow, make_uint4(gflag | gtot.x, gflag | gtot.y, gflag | gtot.z, gflag | gtot.w));
+            if (group > 0) {
+                uint32_t gprev[4] = {0, 0, 0, 0};
+                chain_walk<kPPWindow>(grow - kRadixBins, group, gprev);
+                if (last_of_group)
+                    st_relaxed_gpu_v4(grow, make_uint4(kFlagIncl | ((gprev[0] + gtot.x) & kValueMask),
+                                                       kFlagIncl | ((gprev[1] + gtot.y) & kValueMask),
+                                                       kFlagIncl | ((gprev[2] + gtot.z) & kValueMask),
+                                                       kFlagIncl | ((gprev[3] + gtot.w) & kValueMask)));
 #pragma unroll
-                    for (int j = 0; j < W; ++j)
-                        win[j] = (tile >= back + j) ? ld_relaxed_gpu_v4(row - (size_t)(back + j) * kRadixBins)
-                                                    : make_uint4(kFlagIncl, kFlagIncl, kFlagIncl, kFlagIncl);
-#pragma unroll
-                    for (int j = 0; j < W; ++j) {
-                        const uint32_t w4[4] = {win[j].x, win[j].y, win[j].z, win[j].w};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (!done[k] && need[k] == back + j) {
-                                const uint32_t f = w4[k] & ~kValueMask;
-                                if (f != 0) {
-                                    prev[k] += w4[k] & kValueMask;
-                                    need[k] += 1;
-                                    done[k] = (f == kFlagIncl);
-                                }
-                            }
-                        }
-                    }
-                    if (done[0] && done[1] && done[2] && done[3]) break;
-                    uint32_t nb = 0xFFFFFFFFu;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (!done[k] && need[k] < nb) nb = need[k];
-                    back = nb;
-                }
-                st_relaxed_gpu_v4(row, make_uint4(kFlagIncl | ((prev[0] + tot.x) & kValueMask),
-                                                  kFlagIncl | ((prev[1] + tot.y) & kValueMask),
-                                                  kFlagIncl | ((prev[2] + tot.z) & kValueMask),
-                                                  kFlagIncl | ((prev[3] + tot.w) & kValueMask)));
+                for (int k = 0; k < 4; ++k) prev[k] += gprev[k];
             }
             __syncwarp();
             bar_sync(kBarTstart + b, kRadixBins + kPPChain);
@@ -961,6 +1001,11 @@ int ensure_hist_attr() {
     return B200SORT_OK;
 }
 
+// status rows a pass needs: one per tile, plus (pipelined kernel) one per group of tiles
+size_t status_rows(const Variant &var, size_t tiles) {
+    return var.cluster == 0 ? tiles + div_up(tiles, (size_t)kPPGroup) : tiles;
+}
+
 int launch_onesweep(const Variant &var, size_t tiles, cudaStream_t s, const int32_t *in, int32_t *out,
                     int32_t *tmp, size_t n, int pass, RadixControl *ctl, uint32_t *cur, uint32_t *next,
                     int follow_plan) {
@@ -1023,7 +1068,8 @@ const char *radix_effective_variant_name() { return kVariants[effective_variant(
 
 size_t radix_workspace_bytes(size_t n) {
     const size_t tiles = div_up(n > 0 ? n : 1, kRadixMinTile);
-    return kRadixControlBytes + 2 * tiles * kRadixBins * sizeof(uint32_t);
+    const size_t rows = tiles + div_up(tiles, (size_t)kPPGroup) + 1;
+    return kRadixControlBytes + 2 * rows * kRadixBins * sizeof(uint32_t);
 }
 
 int radix_histogram(const int32_t *d_keys, size_t n, uint32_t *d_hist, cudaStream_t s) {
@@ -1063,7 +1109,7 @@ int radix_single_pass(const int32_t *d_in, int32_t *d_out, size_t n, int pass, v
     const size_t tiles = div_up(n, (size_t)var.tile);
     B200_CUDA_TRY(cudaMemsetAsync(ctl, 0, kRadixZeroBytes, s));
     radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_in, n, ctl, status0,
-                                                                 tiles * kRadixBins, 0, 0);
+                                                                 status_rows(var, tiles) * kRadixBins, 0, 0);
     B200_LAUNCH_CHECK();
     B200_TRY(launch_onesweep(var, tiles, s, d_in, d_out, nullptr, n, pass, ctl, status0, nullptr, 0));
     return B200SORT_OK;
@@ -1110,16 +1156,17 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
     const Variant &var = kVariants[v];
     auto *ctl = static_cast<RadixControl *>(d_ws);
     const size_t tiles = div_up(n, (size_t)var.tile);
+    const size_t rows = status_rows(var, tiles);
     uint32_t *status[2];
     status[0] = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(d_ws) + kRadixControlBytes);
-    status[1] = status[0] + tiles * kRadixBins;
+    status[1] = status[0] + rows * kRadixBins;
     const int skip = g_skip_enabled.load();
     const uint32_t in_place = (d_in == d_out) ? 1u : 0u;
     StepTimer timer{s, ms};
 
     B200_CUDA_TRY(cudaMemsetAsync(ctl, 0, kRadixZeroBytes, s));
     B200_TRY(timer.begin());
-    radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_in, n, ctl, status[0], tiles * kRadixBins,
+    radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_in, n, ctl, status[0], rows * kRadixBins,
                                                                  (uint32_t)skip, in_place);
     B200_LAUNCH_CHECK();
     B200_TRY(timer.mark());
