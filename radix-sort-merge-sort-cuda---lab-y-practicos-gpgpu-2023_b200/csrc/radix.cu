@@ -75,6 +75,7 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
     extern __shared__ __align__(16) uint32_t sh[];
     __shared__ uint32_t s_warp_sums[kRadixBins / 32];
     __shared__ uint32_t s_skip[kRadixPasses];
+    __shared__ uint32_t s_hot[kRadixPasses];
     __shared__ uint32_t s_is_last;
 
     const uint32_t tid = threadIdx.x;
@@ -133,7 +134,7 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
     __threadfence();
     __syncthreads();
     if (tid == 0) s_is_last = (atomicAdd(&ctl->hist_blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;
-    if (tid < kRadixPasses) s_skip[tid] = 0;
+    if (tid < kRadixPasses) { s_skip[tid] = 0; s_hot[tid] = 0; }
     __syncthreads();
     if (!s_is_last) return;
     __threadfence();
@@ -154,6 +155,7 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
             for (uint32_t w = 0; w < warp; ++w) add += s_warp_sums[w];
             ctl->base[p][tid] = x - c + add;
             if (skip_enabled && n > 0 && c == (uint32_t)n) s_skip[p] = 1;
+            if ((size_t)c * 8 > n) s_hot[p] = 1;
         }
         __syncthreads();
     }
@@ -168,6 +170,7 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
         uint32_t j = 0, cur = kSelIn;
         for (int p = 0; p < kRadixPasses; ++p) {
             ctl->skip[p] = s_skip[p];
+            ctl->hot[p] = s_hot[p];
             ctl->src_sel[p] = cur;
             uint32_t dst = cur;
             if (!s_skip[p]) {
@@ -313,11 +316,32 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     {
         uint32_t *wt = s_table + warp * kRadixBins * TW;
         const uint32_t lt = lanemask_lt();
+        // "hot" = some digit value is frequent: globally (the histogram kernel saw one bin with more
+        // than 1/8 of the keys) or in this warp's part of the tile (sorted / clustered input: a
+        // quarter of the lanes agree with lane 0 on the first key).  Warp-uniform.
+        bool hot = false;
+        if (MODE == kRankAdd) {
+            const uint32_t d0 = digit_of(key[0], shift, flip);
+            const uint32_t agree = __ballot_sync(0xffffffffu, d0 == __shfl_sync(0xffffffffu, d0, 0));
+            hot = (follow_plan && ctl->hot[pass] != 0) || __popc(agree) >= 8;
+        }
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const uint32_t d = digit_of(key[i], shift, flip);
             if (MODE == kRankAdd) {
-                const uint32_t r = atomicAdd(wt + d, 1u);
+                uint32_t r;
+                if (!hot) {
+                    r = atomicAdd(wt + d, 1u);
+                } else {
+                    // A digit value is frequent in this pass: same-address atomics would serialise.
+                    // The lanes that share lane 0's digit are ranked with one ballot and ONE atomic.
+                    const bool same = (d == __shfl_sync(0xffffffffu, d, 0));
+                    const uint32_t sm = __ballot_sync(0xffffffffu, same);
+                    r = 0;
+                    if (!same || lane == 0) r = atomicAdd(wt + d, lane == 0 ? (uint32_t)__popc(sm) : 1u);
+                    const uint32_t r0 = __shfl_sync(0xffffffffu, r, 0);
+                    if (same) r = r0 + __popc(sm & lt);
+                }
                 rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
             } else if (MODE == kRankAtomic) {
                 atomicOr(wt + 2 * d, 1u << lane);
@@ -414,11 +438,12 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             run += c;
         }
         s_tstart[tid] = tile_start;
-        if (kSplit) { __threadfence_block(); asm volatile("bar.arrive 3, 512;" ::: "memory"); }
+        if (kSplit) { __threadfence_block(); asm volatile("bar.arrive 3, %0;" :: "n"(WARPS * 32) : "memory"); }
         asm volatile("bar.sync 1, 256;" ::: "memory");      // every (warp, digit) position is final
         if (CL > 1) { cluster_wait(); cluster_arrive(); }    // finish #1; #2: nothing to announce
     }
     if (CL > 1 && !in_a && !in_b) { cluster_arrive(); cluster_wait(); cluster_arrive(); }
+    if (kSplit && !in_a && !in_b) asm volatile("bar.sync 3, %0;" :: "n"(WARPS * 32) : "memory");   // warps 16..: wait for the positions
     if (in_b) {
         if (kSplit) asm volatile("bar.sync 2, 512;" ::: "memory");
         uint32_t total = s_total[bd];                        // my tile; becomes my link's total
@@ -483,13 +508,12 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             cluster_wait();
             if (!looker) prev = s_prev[bd];
         }
-        if (kSplit) asm volatile("bar.sync 3, 512;" ::: "memory");
+        if (kSplit) asm volatile("bar.sync 3, %0;" :: "n"(WARPS * 32) : "memory");
         s_gofs[bd] = digit_base + prev + before - s_tstart[bd];
     }
     // Positions must be final before anybody stages keys: group A knows (its barrier 1), group B
     // knows (barrier 3); a CTA that is not split simply synchronises.
-    static_assert(!kSplit || WARPS == 16, "a split CTA is exactly groups A and B");
-    static_assert(CL == 1 || kSplit, "clustered shapes use the split layout");
+    static_assert(CL == 1 || WARPS == 16, "clustered shapes are exactly groups A and B");
     if (!kSplit) __syncthreads();
 
     // ---- stage the keys in shared memory in digit order ---------------------------------------------
@@ -951,6 +975,10 @@ const Variant kVariants[] = {
     B200_PP_VARIANT(16),                       // 20: 7168
     B200_PP_VARIANT(24),                       // 21: 10752
     B200_PP_VARIANT(18),                       // 22: 8064
+    B200_VARIANT(32, 10, 2, kRankAdd, 1),      // 23: 1024 threads x 10 keys, 2 CTAs/SM = full occupancy, 32 regs
+    B200_VARIANT(32, 8, 2, kRankAdd, 1),       // 24: 8192
+    B200_VARIANT(32, 12, 1, kRankAdd, 1),      // 25: 12288, 1 CTA/SM
+    B200_VARIANT(24, 12, 2, kRankAdd, 1),      // 26: 768 threads x 12 = 9216, 2 CTAs/SM (42 regs)
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
