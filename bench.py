@@ -281,7 +281,7 @@ def ours_single(args) -> None:
             acc[i] += kms[i] / reps
     if algo == ALGO_RADIX:
         pass_ms = [acc[i] for i in range(1, 5)]
-        ran = [p for p in pass_ms if p > 0.02]           # a skipped pass exits in microseconds
+        ran = [p for p in pass_ms if p > 0.25 * max(pass_ms)] if n >= (1 << 22) else pass_ms   # skipped passes exit at once
         kernel_ms = sum(ran) / max(len(ran), 1)
         bytes_per_launch = 8.0 * n
         kernels = {"histogram_ms": acc[0], "pass_ms": pass_ms, "final_copy_ms": acc[5],

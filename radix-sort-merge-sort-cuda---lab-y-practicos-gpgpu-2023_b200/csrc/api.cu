@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 namespace b200sort {
 
@@ -41,8 +43,10 @@ int check_sort_args(const void *keys, const void *tmp, size_t n) {
 }
 
 // ---- the per-process arena behind the host-array operator ---------------------------------------
-constexpr size_t kStageBytes = 16u << 20;      // pinned staging chunk for pageable callers
-constexpr size_t kDirectBytes = 1u << 20;      // below this a plain memcpy is as good as staging
+constexpr size_t kStageBytes = 8u << 20;       // pinned staging chunk for pageable callers
+constexpr size_t kDirectBytes = 4u << 20;      // below this a plain cudaMemcpy is as good as staging
+constexpr int kCopyThreads = 4;                // host threads filling / draining the staging chunks
+constexpr int kStageSlots = 2 * kCopyThreads;  // two chunks per thread: one being copied, one in DMA
 
 struct HostArena {
     std::mutex mu;
@@ -51,19 +55,27 @@ struct HostArena {
     size_t cap_keys = 0;
     void *d_ws = nullptr;
     size_t cap_ws = 0;
-    void *h_stage[2] = {nullptr, nullptr};
+    void *h_stage[kStageSlots] = {};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream[kCopyThreads] = {};
+    cudaEvent_t ev[kStageSlots] = {};
+    cudaEvent_t ev_main = nullptr;
 
     void release() {
         if (d_keys) cudaFree(d_keys);
         if (d_tmp) cudaFree(d_tmp);
         if (d_ws) cudaFree(d_ws);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kStageSlots; ++i) {
             if (h_stage[i]) cudaFreeHost(h_stage[i]);
             if (ev[i]) cudaEventDestroy(ev[i]);
             h_stage[i] = nullptr; ev[i] = nullptr;
         }
+        for (int i = 0; i < kCopyThreads; ++i) {
+            if (copy_stream[i]) cudaStreamDestroy(copy_stream[i]);
+            copy_stream[i] = nullptr;
+        }
+        if (ev_main) cudaEventDestroy(ev_main);
+        ev_main = nullptr;
         if (stream) cudaStreamDestroy(stream);
         d_keys = d_tmp = nullptr; d_ws = nullptr; stream = nullptr;
         cap_keys = cap_ws = 0; device = -1;
@@ -75,7 +87,10 @@ struct HostArena {
         if (dev != device) { release(); device = dev; }
         if (stream == nullptr) {
             B200_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-            for (int i = 0; i < 2; ++i) B200_CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+            for (int i = 0; i < kCopyThreads; ++i)
+                B200_CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream[i], cudaStreamNonBlocking));
+            for (int i = 0; i < kStageSlots; ++i) B200_CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+            B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
         }
         if (n > cap_keys) {
             if (d_keys) cudaFree(d_keys);
@@ -97,7 +112,7 @@ struct HostArena {
     }
 
     int ensure_stage() {
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < kStageSlots; ++i)
             if (h_stage[i] == nullptr) B200_CUDA_TRY(cudaMallocHost(&h_stage[i], kStageBytes));
         return B200SORT_OK;
     }
@@ -114,24 +129,74 @@ bool is_device_accessible_host(const void *p) {
     return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
 }
 
-// Pageable -> device through two pinned chunks: the CPU fills one while the DMA drains the other.
+// Pageable host memory <-> device through pinned staging chunks.  kCopyThreads host threads each
+// own two chunks and a copy stream: while the DMA engine drains one chunk the thread fills the
+// other, so the transfer runs at PCIe speed instead of at one core's memcpy speed (what the
+// reference pays inside cudaMemcpy on a malloc'd array, SRM/lab.cu:321,397).
+int staged_copy(HostArena &a, char *dev, char *host, size_t bytes, bool to_device) {
+    B200_TRY(a.ensure_stage());
+    int dev_id = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev_id));
+    // the copy streams start after everything queued on the main stream so far (e.g. the sort)
+    B200_CUDA_TRY(cudaEventRecord(a.ev_main, a.stream));
+    const size_t chunks = div_up(bytes, kStageBytes);
+    int status[kCopyThreads] = {};
+    cudaError_t cuda_err[kCopyThreads] = {};
+    auto worker = [&](int t) {
+        auto fail = [&](cudaError_t e) { status[t] = B200SORT_ERR_CUDA; cuda_err[t] = e; };
+        cudaError_t e = cudaSetDevice(dev_id);
+        if (e != cudaSuccess) return fail(e);
+        cudaStream_t cs = a.copy_stream[t];
+        if ((e = cudaStreamWaitEvent(cs, a.ev_main, 0)) != cudaSuccess) return fail(e);
+        size_t k = 0;
+        size_t prev_c = (size_t)-1;
+        int prev_slot = 0;
+        for (size_t c = t; c < chunks; c += kCopyThreads, ++k) {
+            const int slot = 2 * t + (int)(k & 1);
+            const size_t off = c * kStageBytes;
+            const size_t len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+            if (to_device) {
+                if ((e = cudaEventSynchronize(a.ev[slot])) != cudaSuccess) return fail(e);   // chunk free again
+                std::memcpy(a.h_stage[slot], host + off, len);
+                if ((e = cudaMemcpyAsync(dev + off, a.h_stage[slot], len, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return fail(e);
+                if ((e = cudaEventRecord(a.ev[slot], cs)) != cudaSuccess) return fail(e);
+            } else {
+                if ((e = cudaMemcpyAsync(a.h_stage[slot], dev + off, len, cudaMemcpyDeviceToHost, cs)) != cudaSuccess) return fail(e);
+                if ((e = cudaEventRecord(a.ev[slot], cs)) != cudaSuccess) return fail(e);
+                if (prev_c != (size_t)-1) {       // drain the previous chunk while this one is in flight
+                    const size_t poff = prev_c * kStageBytes;
+                    const size_t plen = bytes - poff < kStageBytes ? bytes - poff : kStageBytes;
+                    if ((e = cudaEventSynchronize(a.ev[prev_slot])) != cudaSuccess) return fail(e);
+                    std::memcpy(host + poff, a.h_stage[prev_slot], plen);
+                }
+                prev_c = c;
+                prev_slot = slot;
+            }
+        }
+        if (!to_device && prev_c != (size_t)-1) {
+            const size_t poff = prev_c * kStageBytes;
+            const size_t plen = bytes - poff < kStageBytes ? bytes - poff : kStageBytes;
+            if ((e = cudaEventSynchronize(a.ev[prev_slot])) != cudaSuccess) return fail(e);
+            std::memcpy(host + poff, a.h_stage[prev_slot], plen);
+        }
+        if (to_device && (e = cudaStreamSynchronize(cs)) != cudaSuccess) return fail(e);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < kCopyThreads; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto &th : pool) th.join();
+    for (int t = 0; t < kCopyThreads; ++t)
+        if (status[t] != B200SORT_OK) return record_cuda(cuda_err[t]);
+    return B200SORT_OK;
+}
+
 int h2d(HostArena &a, int32_t *d, const int32_t *h, size_t bytes) {
     if (bytes <= kDirectBytes || is_device_accessible_host(h)) {
         B200_CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, a.stream));
         return B200SORT_OK;
     }
-    B200_TRY(a.ensure_stage());
-    const char *src = reinterpret_cast<const char *>(h);
-    char *dst = reinterpret_cast<char *>(d);
-    int slot = 0;
-    for (size_t off = 0; off < bytes; off += kStageBytes, slot ^= 1) {
-        const size_t len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
-        B200_CUDA_TRY(cudaEventSynchronize(a.ev[slot]));       // previous DMA out of this chunk done
-        std::memcpy(a.h_stage[slot], src + off, len);
-        B200_CUDA_TRY(cudaMemcpyAsync(dst + off, a.h_stage[slot], len, cudaMemcpyHostToDevice, a.stream));
-        B200_CUDA_TRY(cudaEventRecord(a.ev[slot], a.stream));
-    }
-    return B200SORT_OK;
+    // every chunk has landed when this returns, so the main stream needs no further dependency
+    return staged_copy(a, reinterpret_cast<char *>(d), reinterpret_cast<char *>(const_cast<int32_t *>(h)), bytes, true);
 }
 
 int d2h(HostArena &a, int32_t *h, const int32_t *d, size_t bytes) {
@@ -140,25 +205,7 @@ int d2h(HostArena &a, int32_t *h, const int32_t *d, size_t bytes) {
         B200_CUDA_TRY(cudaStreamSynchronize(a.stream));
         return B200SORT_OK;
     }
-    B200_TRY(a.ensure_stage());
-    char *dst = reinterpret_cast<char *>(h);
-    const char *src = reinterpret_cast<const char *>(d);
-    const size_t chunks = div_up(bytes, kStageBytes);
-    for (size_t c = 0; c <= chunks; ++c) {
-        if (c < chunks) {
-            const size_t off = c * kStageBytes;
-            const size_t len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
-            B200_CUDA_TRY(cudaMemcpyAsync(a.h_stage[c & 1], src + off, len, cudaMemcpyDeviceToHost, a.stream));
-            B200_CUDA_TRY(cudaEventRecord(a.ev[c & 1], a.stream));
-        }
-        if (c > 0) {
-            const size_t off = (c - 1) * kStageBytes;
-            const size_t len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
-            B200_CUDA_TRY(cudaEventSynchronize(a.ev[(c - 1) & 1]));
-            std::memcpy(dst + off, a.h_stage[(c - 1) & 1], len);
-        }
-    }
-    return B200SORT_OK;
+    return staged_copy(a, reinterpret_cast<char *>(const_cast<int32_t *>(d)), reinterpret_cast<char *>(h), bytes, false);
 }
 
 int sort_dispatch(int algo, const int32_t *in, int32_t *out, int32_t *t, size_t n, void *ws, size_t wsb,

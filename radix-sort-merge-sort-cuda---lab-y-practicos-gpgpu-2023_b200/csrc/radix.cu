@@ -325,23 +325,26 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             const uint32_t agree = __ballot_sync(0xffffffffu, d0 == __shfl_sync(0xffffffffu, d0, 0));
             hot = (follow_plan && ctl->hot[pass] != 0) || __popc(agree) >= 8;
         }
+        if (MODE == kRankAdd && !hot) {
+            // the common case, kept free of any per-key branch
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const uint32_t r = atomicAdd(wt + digit_of(key[i], shift, flip), 1u);
+                rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
+            }
+        } else {
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const uint32_t d = digit_of(key[i], shift, flip);
             if (MODE == kRankAdd) {
-                uint32_t r;
-                if (!hot) {
-                    r = atomicAdd(wt + d, 1u);
-                } else {
-                    // A digit value is frequent in this pass: same-address atomics would serialise.
-                    // The lanes that share lane 0's digit are ranked with one ballot and ONE atomic.
-                    const bool same = (d == __shfl_sync(0xffffffffu, d, 0));
-                    const uint32_t sm = __ballot_sync(0xffffffffu, same);
-                    r = 0;
-                    if (!same || lane == 0) r = atomicAdd(wt + d, lane == 0 ? (uint32_t)__popc(sm) : 1u);
-                    const uint32_t r0 = __shfl_sync(0xffffffffu, r, 0);
-                    if (same) r = r0 + __popc(sm & lt);
-                }
+                // A digit value is frequent: same-address atomics would serialise.  The lanes that
+                // share lane 0's digit are ranked with one ballot and ONE atomic.
+                const bool same = (d == __shfl_sync(0xffffffffu, d, 0));
+                const uint32_t sm = __ballot_sync(0xffffffffu, same);
+                uint32_t r = 0;
+                if (!same || lane == 0) r = atomicAdd(wt + d, lane == 0 ? (uint32_t)__popc(sm) : 1u);
+                const uint32_t r0 = __shfl_sync(0xffffffffu, r, 0);
+                if (same) r = r0 + __popc(sm & lt);
                 rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
             } else if (MODE == kRankAtomic) {
                 atomicOr(wt + 2 * d, 1u << lane);
@@ -374,6 +377,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
                 const uint32_t r = before + __popc(lower);
                 rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
             }
+        }
         }
     }
     __syncthreads();
