@@ -226,7 +226,7 @@ def ours_single(args) -> None:
     torch.cuda.set_device(0)
     dev = torch.device("cuda:0")
     check(L.b200sort_device_check())
-    algo = ALGO_RADIX if args.algo == "radix" else ALGO_MERGE
+    algo = {"radix": ALGO_RADIX, "merge": ALGO_MERGE, "lab": 2}[args.algo]
     n = 1 << args.log2n
     if args.variant is not None:
         check(L.b200sort_radix_set_variant(args.variant))
@@ -369,7 +369,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--algo", default="radix", choices=["radix", "merge"])
+    ap.add_argument("--algo", default="radix", choices=["radix", "merge", "lab"])
     ap.add_argument("--dist", default="uniform")
     ap.add_argument("--log2n", type=int, default=28)
     ap.add_argument("--variant", type=int, default=None, help="onesweep tile shape (sweeps only)")

@@ -76,6 +76,10 @@ int    b200sort_radix_i32(int32_t *d_keys, int32_t *d_tmp, size_t n,
                           void *d_ws, size_t ws_bytes, void *stream);
 int    b200sort_merge_i32(int32_t *d_keys, int32_t *d_tmp, size_t n,
                           void *d_ws, size_t ws_bytes, void *stream);
+/* The assignment's staged pipeline (SRM/letra.pdf p.3 parts a-d, SRM/lab.cu:303-402) as a third
+ * algorithm: 1-bit warp split on 32-key groups -> in-block rank merges -> merge-path merges. */
+int    b200sort_lab_i32(int32_t *d_keys, int32_t *d_tmp, size_t n,
+                        void *d_ws, size_t ws_bytes, void *stream);
 int    b200sort_sort_i32(int algo, int32_t *d_keys, int32_t *d_tmp, size_t n,
                          void *d_ws, size_t ws_bytes, void *stream);
 /* Out-of-place form: d_out = sorted d_in; d_in is only read (it may also equal d_out).  No extra
@@ -100,6 +104,8 @@ int b200sort_radix_pass_i32(const int32_t *d_in, int32_t *d_out, size_t n, int p
 /* Keys per tile of the block sort (every aligned run of this many keys comes out sorted). */
 size_t b200sort_block_sort_tile(void);
 int b200sort_block_sort_i32(const int32_t *d_in, int32_t *d_out, size_t n, void *stream);
+/* Same contract, produced by the lab's stages 1-2 (warp split + rank merges; SRM/lab.cu:47-197). */
+int b200sort_lab_tile_sort_i32(const int32_t *d_in, int32_t *d_out, size_t n, void *stream);
 /* Keys per output tile of a merge pass. */
 size_t b200sort_merge_tile(void);
 /* Merge-path split points for one pass over sorted runs of `run` keys (run a multiple of

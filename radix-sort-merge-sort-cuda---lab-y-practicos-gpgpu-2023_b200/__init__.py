@@ -7,9 +7,9 @@ package is the thin host-side mirror of that interface used by the tests, the dr
 bench.py.  There is no CPU fallback anywhere: every sort call fails loudly without the CUDA
 library or without an sm_100 device.
 """
-from ._lib import (ALGO_MERGE, ALGO_RADIX, B200SortError, lib, lib_path, check)  # noqa: F401
+from ._lib import (ALGO_LAB, ALGO_MERGE, ALGO_RADIX, B200SortError, lib, lib_path, check)  # noqa: F401
 from .lab import order_array, order_with_trust  # noqa: F401
 from . import datagen  # noqa: F401
 
 __all__ = ["order_array", "order_with_trust", "lib", "lib_path", "B200SortError",
-           "ALGO_RADIX", "ALGO_MERGE", "datagen"]
+           "ALGO_RADIX", "ALGO_MERGE", "ALGO_LAB", "datagen"]

@@ -9,6 +9,7 @@ _LIB_NAME = "libb200sort.so"
 
 ALGO_RADIX = 0
 ALGO_MERGE = 1
+ALGO_LAB = 2
 MAX_N = 1 << 30
 
 _STATUS = {0: "ok", 1: "invalid argument", 2: "workspace", 3: "CUDA runtime error",
@@ -36,6 +37,8 @@ SIGNATURES = {
     "b200sort_workspace_bytes": (_sz, [_sz, _i]),
     "b200sort_radix_i32": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "b200sort_merge_i32": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "b200sort_lab_i32": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "b200sort_lab_tile_sort_i32": (_i, [_vp, _vp, _sz, _vp]),
     "b200sort_sort_i32": (_i, [_i, _vp, _vp, _sz, _vp, _sz, _vp]),
     "b200sort_sort_copy_i32": (_i, [_i, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "b200sort_sort_timed_i32": (_i, [_i, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),

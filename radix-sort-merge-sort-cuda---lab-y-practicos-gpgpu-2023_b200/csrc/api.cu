@@ -213,7 +213,8 @@ int sort_dispatch(int algo, const int32_t *in, int32_t *out, int32_t *t, size_t 
     switch (algo) {
         case B200SORT_ALGO_RADIX: return ms ? radix_sort_timed(in, out, t, n, ws, wsb, s, ms)
                                             : radix_sort(in, out, t, n, ws, wsb, s);
-        case B200SORT_ALGO_MERGE: return merge_sort(in, out, t, n, ws, wsb, s, ms);
+        case B200SORT_ALGO_MERGE: return merge_sort(in, out, t, n, ws, wsb, s, ms, false);
+        case B200SORT_ALGO_LAB: return merge_sort(in, out, t, n, ws, wsb, s, ms, true);
         default: return B200SORT_ERR_INVALID;
     }
 }
@@ -221,14 +222,16 @@ int sort_dispatch(int algo, const int32_t *in, int32_t *out, int32_t *t, size_t 
 size_t workspace_bytes(size_t n, int algo) {
     switch (algo) {
         case B200SORT_ALGO_RADIX: return radix_workspace_bytes(n);
-        case B200SORT_ALGO_MERGE: return merge_workspace_bytes(n);
+        case B200SORT_ALGO_MERGE:
+        case B200SORT_ALGO_LAB: return merge_workspace_bytes(n);
         default: return 0;
     }
 }
 
 int order_host(int32_t *h_keys, size_t n, int algo) {
     if (n > B200SORT_MAX_N) return B200SORT_ERR_INVALID;
-    if (algo != B200SORT_ALGO_RADIX && algo != B200SORT_ALGO_MERGE) return B200SORT_ERR_INVALID;
+    if (algo != B200SORT_ALGO_RADIX && algo != B200SORT_ALGO_MERGE && algo != B200SORT_ALGO_LAB)
+        return B200SORT_ERR_INVALID;
     if (n <= 1) return B200SORT_OK;
     if (h_keys == nullptr) return B200SORT_ERR_INVALID;
     B200_TRY(device_check());
@@ -281,6 +284,11 @@ int b200sort_merge_i32(int32_t *d_keys, int32_t *d_tmp, size_t n, void *d_ws, si
     return merge_sort(d_keys, d_keys, d_tmp, n, d_ws, ws_bytes, static_cast<cudaStream_t>(stream), nullptr);
 }
 
+int b200sort_lab_i32(int32_t *d_keys, int32_t *d_tmp, size_t n, void *d_ws, size_t ws_bytes, void *stream) {
+    B200_TRY(check_sort_args(d_keys, d_tmp, n));
+    return merge_sort(d_keys, d_keys, d_tmp, n, d_ws, ws_bytes, static_cast<cudaStream_t>(stream), nullptr, true);
+}
+
 int b200sort_sort_i32(int algo, int32_t *d_keys, int32_t *d_tmp, size_t n, void *d_ws, size_t ws_bytes,
                       void *stream) {
     B200_TRY(check_sort_args(d_keys, d_tmp, n));
@@ -315,7 +323,11 @@ int b200sort_radix_pass_i32(const int32_t *d_in, int32_t *d_out, size_t n, int p
 size_t b200sort_block_sort_tile(void) { return merge_block_tile(); }
 int b200sort_block_sort_i32(const int32_t *d_in, int32_t *d_out, size_t n, void *stream) {
     if (n > B200SORT_MAX_N || (n > 0 && (d_in == nullptr || d_out == nullptr))) return B200SORT_ERR_INVALID;
-    return merge_block_sort(d_in, d_out, n, static_cast<cudaStream_t>(stream));
+    return merge_block_sort(d_in, d_out, n, static_cast<cudaStream_t>(stream), false);
+}
+int b200sort_lab_tile_sort_i32(const int32_t *d_in, int32_t *d_out, size_t n, void *stream) {
+    if (n > B200SORT_MAX_N || (n > 0 && (d_in == nullptr || d_out == nullptr))) return B200SORT_ERR_INVALID;
+    return merge_block_sort(d_in, d_out, n, static_cast<cudaStream_t>(stream), true);
 }
 size_t b200sort_merge_tile(void) { return merge_tile(); }
 int b200sort_merge_partition_i32(const int32_t *d_in, size_t n, size_t run, uint32_t *d_splits, void *stream) {

@@ -130,6 +130,77 @@ block_sort_kernel(const int32_t *in, int32_t *out, size_t n)
 }
 
 // ------------------------------------------------------------------------------------------------
+// k3-lab: the assignment's staged tile sort (parts a-c of SRM/letra.pdf p.3), kept as a third way to
+// produce sorted 4096-key tiles:
+//   stage 1  every warp sorts 32-key groups with the LSD "split" primitive, one bit per iteration
+//            (SRM/lab.cu:47-87).  The exclusive scan of the flags (SRM/lab.cu:11-41, 15 shuffles) is
+//            one __ballot_sync + two __popc; bit 31 is split with inverted sense so that the order
+//            is signed; the loop exits as soon as the group is sorted (SRM/lab.cu:61).
+//   stage 2  rank merges of neighbouring runs 32 -> 64 -> ... -> 4096 in shared memory: every key
+//            binary-searches the sibling run (SRM/lab.cu:102-132) and lands at own index + rank,
+//            A before equal B's (SRM/lab.cu:144-182, :192-197) -- here up to 4096 per block, not 512.
+// Stage 3 (runs longer than a block, SRM/lab.cu:209-300) is the merge-path pair k4/k5 below.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads)
+lab_tile_sort_kernel(const int32_t *in, int32_t *out, size_t n)
+{
+    __shared__ int32_t buf[2][kSortTile];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t tile_base = (size_t)blockIdx.x * kSortTile;
+    const uint32_t valid = (n - tile_base < (size_t)kSortTile) ? (uint32_t)(n - tile_base) : (uint32_t)kSortTile;
+    const uint32_t lt = lanemask_lt();
+
+    // stage 1: each warp takes groups warp, warp+8, ... of 32 consecutive keys
+    for (uint32_t g = warp; g < kSortTile / 32; g += kSortThreads / 32) {
+        const uint32_t i = g * 32 + lane;
+        int32_t key = (i < valid) ? ld_stream(in + tile_base + i) : 0x7FFFFFFF;     // padding sorts last
+        int32_t *swap = buf[0] + g * 32;
+        for (int bit = 0; bit < 32; ++bit) {
+            int32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+            if (lane == 0) prev = key;
+            if (__all_sync(0xffffffffu, prev <= key)) break;                        // sorted: done
+            const bool set = (static_cast<uint32_t>(key) >> bit) & 1u;
+            const bool first = (bit == 31) ? set : !set;                            // who goes in front
+            const uint32_t front = __ballot_sync(0xffffffffu, first);
+            const uint32_t f = __popc(front & lt);                                  // exclusive scan of the flags
+            const uint32_t dst = first ? f : lane - f + __popc(front);              // the split rule
+            swap[dst] = key;
+            __syncwarp();
+            key = swap[lane];
+            __syncwarp();
+        }
+        swap[lane] = key;
+    }
+    __syncthreads();
+
+    // stage 2: rank merges, ping-pong between the two buffers
+    int cur = 0;
+    for (uint32_t len = 32; len < (uint32_t)kSortTile; len <<= 1) {
+        const int32_t *src = buf[cur];
+        int32_t *dst = buf[cur ^ 1];
+#pragma unroll 4
+        for (uint32_t i = tid; i < (uint32_t)kSortTile; i += kSortThreads) {
+            const uint32_t pair = i & ~(2 * len - 1);
+            const bool from_b = (i & len) != 0;
+            const int32_t x = src[i];
+            const int32_t *other = src + pair + (from_b ? 0 : len);
+            // rank of x in the sibling run: lower bound for A's keys, upper bound for B's keys
+            uint32_t lo = 0, hi = len;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const int32_t y = other[mid];
+                const bool down = from_b ? (x < y) : (x <= y);
+                if (down) hi = mid; else lo = mid + 1;
+            }
+            dst[pair + (i & (len - 1)) + lo] = x;
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    for (uint32_t i = tid; i < valid; i += kSortThreads) st_stream(out + tile_base + i, buf[cur][i]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k4
 // ------------------------------------------------------------------------------------------------
 struct PairGeom { size_t base; size_t la; size_t lb; };
@@ -223,9 +294,12 @@ size_t merge_workspace_bytes(size_t n) {
     return align_up((div_up(n > 0 ? n : 1, kSortTile) + 2) * sizeof(uint32_t), 256);
 }
 
-int merge_block_sort(const int32_t *d_in, int32_t *d_out, size_t n, cudaStream_t s) {
+int merge_block_sort(const int32_t *d_in, int32_t *d_out, size_t n, cudaStream_t s, bool lab_stages) {
     if (n == 0) return B200SORT_OK;
-    block_sort_kernel<<<(unsigned)div_up(n, kSortTile), kSortThreads, 0, s>>>(d_in, d_out, n);
+    if (lab_stages)
+        lab_tile_sort_kernel<<<(unsigned)div_up(n, kSortTile), kSortThreads, 0, s>>>(d_in, d_out, n);
+    else
+        block_sort_kernel<<<(unsigned)div_up(n, kSortTile), kSortThreads, 0, s>>>(d_in, d_out, n);
     B200_LAUNCH_CHECK();
     return B200SORT_OK;
 }
@@ -249,7 +323,7 @@ int merge_pass(const int32_t *d_in, int32_t *d_out, size_t n, size_t run, const 
 }
 
 int merge_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, void *d_ws,
-               size_t ws_bytes, cudaStream_t s, float *ms) {
+               size_t ws_bytes, cudaStream_t s, float *ms, bool lab_stages) {
     if (ms) ms[0] = ms[1] = ms[2] = 0.f;
     if (n == 0) return B200SORT_OK;
     if (n == 1) {
@@ -269,7 +343,7 @@ int merge_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, vo
         for (auto &e : ev) B200_CUDA_TRY(cudaEventCreate(&e));
         B200_CUDA_TRY(cudaEventRecord(ev[0], s));
     }
-    B200_TRY(merge_block_sort(d_in, src, n, s));
+    B200_TRY(merge_block_sort(d_in, src, n, s, lab_stages));
     if (ms) B200_CUDA_TRY(cudaEventRecord(ev[1], s));
     for (size_t run = kSortTile; run < n; run *= 2) {
         B200_TRY(merge_partition(src, n, run, splits, s));

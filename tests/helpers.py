@@ -5,9 +5,9 @@ from __future__ import annotations
 import numpy as np
 
 import b200sort
-from b200sort._lib import ALGO_MERGE, ALGO_RADIX, check, lib
+from b200sort._lib import ALGO_LAB, ALGO_MERGE, ALGO_RADIX, check, lib
 
-ALGOS = {"radix": ALGO_RADIX, "merge": ALGO_MERGE}
+ALGOS = {"radix": ALGO_RADIX, "merge": ALGO_MERGE, "lab": ALGO_LAB}
 
 
 def to_device(a: np.ndarray):

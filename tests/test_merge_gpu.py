@@ -87,3 +87,35 @@ def test_full_size_properties_2_28(dist):
     torch.cuda.synchronize()
     assert bool((d[1:] >= d[:-1]).all().item()), "not sorted"
     assert int(d.sum(dtype=torch.int64).item()) == before_sum
+
+
+# ---- the assignment's staged pipeline as a third algorithm (B200SORT_ALGO_LAB) ----------------------
+
+def test_lab_tile_sort_sorts_every_tile():
+    import torch
+    T = lib().b200sort_block_sort_tile()
+    for dist, n in (("uniform", 6 * T), ("edge_mix", 2 * T + 33), ("descending", T), ("lab_rand100", 3000), ("all_equal", 70)):
+        keys = datagen.make(dist, n, 6)
+        d_in = to_device(keys); d_out = torch.empty_like(d_in)
+        check(lib().b200sort_lab_tile_sort_i32(d_in.data_ptr(), d_out.data_ptr(), n, stream_ptr()))
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        for base in range(0, n, T):
+            assert_bit_exact(got[base:base + T], oracle.order_array(keys[base:base + T]), f"{dist} tile@{base}")
+
+
+@pytest.mark.parametrize("dist", ["uniform", "uniform_nonneg", "lab_rand100", "edge_mix", "and3", "descending", "all_equal", "skewed90"])
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 256, 4096, 4097, 65536, 100001, 1 << 20])
+def test_lab_pipeline_bit_exact(dist, n):
+    from b200sort._lib import ALGO_LAB
+    if dist == "lab_rand100" and n > 65536:
+        pytest.skip("slow libc loop")
+    keys = datagen.make(dist, n, 29)
+    want = oracle.order_array(keys) if n <= 1 << 16 else oracle.radix_sort(keys)
+    assert_bit_exact(gpu_sort(keys, ALGO_LAB), want, f"{dist} n={n}")
+
+
+def test_lab_pipeline_golden_vectors(golden_small):
+    from b200sort._lib import ALGO_LAB
+    for name, (keys, ref_out) in golden_small.items():
+        assert_bit_exact(gpu_sort(keys, ALGO_LAB), ref_out, name)
