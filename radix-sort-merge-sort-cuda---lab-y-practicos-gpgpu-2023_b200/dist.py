@@ -126,15 +126,25 @@ class DistSorter:
             L.b200sort_device_free(self.recv_ptr)
             self.recv_ptr = None
 
-    def sort(self, keys):
+    def sort(self, keys, phase_events=None):
         """Sort the distributed array whose local part is the int32 CUDA tensor ``keys`` (read
-        only).  Returns (tensor view of this rank's slice of the global order, its length)."""
+        only).  Returns (tensor view of this rank's slice of the global order, its length).
+        ``phase_events``: optional list that receives CUDA events recorded at the phase boundaries
+        (start, histogram, plan, partition+exchange, local sort)."""
         torch, dist, L = self.torch, self.dist, lib()
+
+        def mark():
+            if phase_events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                phase_events.append(e)
+        mark()
         n = keys.numel()
         assert n <= self.n_local and keys.dtype == torch.int32 and keys.is_cuda and keys.is_contiguous()
         stream = torch.cuda.current_stream().cuda_stream
         # phase 1
         check(L.b200sort_dist_histogram_i32(keys.data_ptr(), n, self.bits, self.hist.data_ptr(), stream))
+        mark()
         # phase 2: counts of every rank (world x nbins, 8 B each: latency-bound); the host planner
         # needs them, so this is the one host synchronisation of the sort
         dist.all_gather_into_tensor(self.all_hist, self.hist, group=self.group)
@@ -145,6 +155,7 @@ class DistSorter:
             raise RuntimeError(f"rank would receive {int(recv.max())} keys, receive buffers hold {self.cap}: "
                                "raise headroom (skewed keys)")
         self.owner_dev.copy_(torch.from_numpy(owner), non_blocking=False)
+        mark()
         # phase 3
         if self.exchange == "p2p":
             base = (ctypes.c_void_p * self.world)(*self.peer_ptrs)
@@ -165,9 +176,11 @@ class DistSorter:
             out_splits = [int(x) for x in send]
             dist.all_to_all_single(self.recv_t[:m], self.send[:n], in_splits, out_splits, group=self.group)
             recv_ptr = self.recv_t.data_ptr()
+        mark()
         # phase 4
         check(L.b200sort_sort_copy_i32(ALGO_RADIX, recv_ptr, self.out.data_ptr(), self.tmp.data_ptr(), m,
                                        self.ws_ptr, self.ws_bytes, stream))
+        mark()
         self.last = {"recv": m, "sent_remote": int(send.sum() - send[self.rank]), "recv_counts": recv}
         return self.out[:m], m
 
@@ -251,6 +264,13 @@ def bench_main(args, metric: str, unit: str, ClockSampler, peaks_fn) -> None:
     total_keys = world * n_local
 
     sent = sorter.last.get("sent_remote", 0)
+    # phase breakdown of one more sort (CUDA events at the phase boundaries, max over ranks)
+    evs = []
+    sorter.sort(src, phase_events=evs)
+    torch.cuda.synchronize()
+    ph = torch.tensor([evs[i].elapsed_time(evs[i + 1]) for i in range(4)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    phases = {k: float(v) for k, v in zip(("msd_histogram_ms", "allgather_plan_ms", "partition_exchange_ms", "local_sort_ms"), ph.tolist())}
 
     # e2e: host buffers in, host buffers out (pinned), every step
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -296,7 +316,8 @@ def bench_main(args, metric: str, unit: str, ClockSampler, peaks_fn) -> None:
                          "kernel": "whole distributed sort per GPU: 4 (MSD histogram) + 8 (partition/exchange) + "
                                    "36 (local sort) = 48 B/key of HBM traffic",
                          "peak_source": peaks["source"],
-                         "nvlink_bytes_sent_per_gpu": 4 * sent},
+                         "nvlink_bytes_sent_per_gpu": 4 * sent, "phases_max_over_ranks": phases,
+                         "nvlink_gbs_per_gpu_out": 4 * sent / (phases["partition_exchange_ms"] / 1e3) / 1e9},
             "cpu_baseline": None,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": 4 * n_local * world,
                     "d2h_bytes_per_step": 4 * n_local * world, "steps": e2e_steps,
