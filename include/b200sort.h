@@ -180,7 +180,8 @@ int b200sort_dist_histogram_i32(const int32_t *d_keys, size_t n, int bits,
 int b200sort_dist_plan(const unsigned long long *all_hist, int world, int rank, int bits,
                        int *bin_owner, unsigned long long *recv_count,
                        unsigned long long *send_count, unsigned long long *dst_offset);
-/* h_dst_base[r]  (HOST array of `world` device-visible pointers) base of rank r's receive buffer;
+/* h_dst_base[r]  (HOST array of `world` device-visible pointers, each 16-byte aligned) base of rank r's
+ *                receive buffer;
  * d_bin_owner    device copy of the planner's bin_owner (int[2^bits]);
  * h_dst_offset   HOST array, the planner's dst_offset;
  * d_ws           b200sort_dist_workspace_bytes(n, bits) bytes, 256-byte aligned. */

@@ -70,18 +70,30 @@ struct DistPartitionArgs {
     unsigned long long dst_offset[kDistMaxWorld];      // where this rank's block starts in it
 };
 
+// Staging area: the tile's keys grouped by destination, with up to 3 pad slots in front of every
+// group so that (slot index - index in the destination buffer) is a multiple of 4.  A 16-byte
+// aligned vector of the staging area then maps to a 16-byte aligned vector of the destination, and
+// the interior of every group leaves with 128-bit stores (4x fewer store instructions and 512-byte
+// instead of 128-byte NVLink writes per warp); only group heads and tails use 32-bit stores.
+constexpr int kDistSlots = kDistTile + 4 * kDistMaxWorld;
+
+__device__ __forceinline__ void st_stream_v4(int32_t *p, int4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __global__ void __launch_bounds__(kDistThreads, 2)
 dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int world,
                       const int *__restrict__ bin_owner, DistPartitionArgs args,
                       unsigned long long *cursor /* [world], zeroed */)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int32_t *s_keys = reinterpret_cast<int32_t *>(smem_raw);                  // [kDistTile]
-    uint8_t *s_dest = reinterpret_cast<uint8_t *>(s_keys + kDistTile);        // [kDistTile]
-    uint8_t *s_owner = s_dest + kDistTile;                                    // [2^bits]
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_owner + (1u << bits));   // [kDistMaxWorld]
-    uint32_t *s_start = s_cnt + kDistMaxWorld;                                // [kDistMaxWorld + 1]
+    int32_t *s_keys = reinterpret_cast<int32_t *>(smem_raw);                  // [kDistSlots]
+    uint8_t *s_dest = reinterpret_cast<uint8_t *>(s_keys + kDistSlots);       // [kDistSlots], 0xFF = pad
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_dest + kDistSlots);      // [kDistMaxWorld]
+    uint32_t *s_start = s_cnt + kDistMaxWorld;                                // [kDistMaxWorld + 2]
     unsigned long long *s_gbase = reinterpret_cast<unsigned long long *>(s_start + kDistMaxWorld + 2);
+    uint8_t *s_owner = reinterpret_cast<uint8_t *>(s_gbase + kDistMaxWorld);  // [2^bits]
 
     const uint32_t tid = threadIdx.x;
     const uint32_t nbins = 1u << bits;
@@ -93,6 +105,8 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
         const size_t base = tile * kDistTile;
         const uint32_t valid = (n - base < (size_t)kDistTile) ? (uint32_t)(n - base) : (uint32_t)kDistTile;
         if (tid < kDistMaxWorld) s_cnt[tid] = 0;
+        for (uint32_t i = tid; i < kDistSlots / 16; i += kDistThreads)         // every slot starts as a pad
+            reinterpret_cast<uint4 *>(s_dest)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
         __syncthreads();                               // also: s_owner ready, previous tile drained
 
         int32_t key[kDistIpt];
@@ -111,13 +125,19 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
             }
         }
         __syncthreads();
+        if (tid < (uint32_t)world)                     // reserve this tile's share of every destination
+            s_gbase[tid] = args.dst_offset[tid] +
+                           (s_cnt[tid] ? atomicAdd(&cursor[tid], (unsigned long long)s_cnt[tid]) : 0ull);
+        __syncthreads();
         if (tid == 0) {
             uint32_t run = 0;
-            for (int d = 0; d < world; ++d) { s_start[d] = run; run += s_cnt[d]; }
+            for (int d = 0; d < world; ++d) {
+                run += ((uint32_t)s_gbase[d] - run) & 3u;          // co-align staging and destination
+                s_start[d] = run;
+                run += s_cnt[d];
+            }
             s_start[world] = run;
         }
-        if (tid < (uint32_t)world && s_cnt[tid] > 0)   // reserve this tile's share of every destination
-            s_gbase[tid] = args.dst_offset[tid] + atomicAdd(&cursor[tid], (unsigned long long)s_cnt[tid]);
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < kDistIpt; ++i) {
@@ -130,12 +150,21 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
             }
         }
         __syncthreads();
+        const uint32_t vectors = (s_start[world] + 3) / 4;
+        for (uint32_t v = tid; v < vectors; v += kDistThreads) {
+            const uint32_t d4 = reinterpret_cast<const uint32_t *>(s_dest)[v];
+            if (d4 == 0xFFFFFFFFu) continue;
+            const uint32_t d0 = d4 & 0xFFu;
+            if (d4 == d0 * 0x01010101u) {
+                const int4 k = reinterpret_cast<const int4 *>(s_keys)[v];
+                st_stream_v4(args.dst_base[d0] + s_gbase[d0] + (4 * v - s_start[d0]), k);
+            } else {
 #pragma unroll
-        for (int i = 0; i < kDistIpt; ++i) {
-            const uint32_t q = i * kDistThreads + tid;
-            if (q < valid) {
-                const uint32_t d = s_dest[q];
-                st_stream(args.dst_base[d] + s_gbase[d] + (q - s_start[d]), s_keys[q]);
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t d = (d4 >> (8 * e)) & 0xFFu;
+                    if (d != 0xFFu)
+                        st_stream(args.dst_base[d] + s_gbase[d] + (4 * v + e - s_start[d]), s_keys[4 * v + e]);
+                }
             }
         }
     }
@@ -145,8 +174,8 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
 size_t dist_workspace_bytes(size_t, int) { return 256; }    // the destination cursors
 
 static size_t partition_smem(int bits) {
-    return (size_t)kDistTile * 4 + kDistTile + ((size_t)1 << bits) + (kDistMaxWorld * 2 + 2) * 4
-           + kDistMaxWorld * 8 + 16;
+    return (size_t)kDistSlots * 4 + kDistSlots + (kDistMaxWorld * 2 + 2) * 4 + kDistMaxWorld * 8
+           + ((size_t)1 << bits) + 16;
 }
 
 int dist_histogram(const int32_t *d_keys, size_t n, int bits, unsigned long long *d_hist, cudaStream_t s) {
@@ -214,6 +243,8 @@ int dist_partition(const int32_t *d_keys, size_t n, int bits, int world, int32_t
         h_dst_base == nullptr || h_dst_offset == nullptr || d_bin_owner == nullptr)
         return B200SORT_ERR_INVALID;
     if (d_ws == nullptr || ws_bytes < dist_workspace_bytes(n, bits)) return B200SORT_ERR_WORKSPACE;
+    for (int r = 0; r < world; ++r)       // 128-bit stores into the destinations
+        if (reinterpret_cast<uintptr_t>(h_dst_base[r]) & 15) return B200SORT_ERR_INVALID;
     if (n == 0) return B200SORT_OK;
     DistPartitionArgs args;
     std::memset(&args, 0, sizeof args);
