@@ -167,6 +167,7 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
                 }
             }
         }
+        __syncthreads();                               // the staging area is reused by the next tile
     }
 }
 

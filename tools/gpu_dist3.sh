@@ -1,8 +1,8 @@
 #!/bin/bash
 N=${1:-2}
 mkdir -p gpurun_out
-echo "== dist kernel tests"; timeout 600 python -m pytest tests/test_dist_gpu.py -m gpu -q -x --timeout 300 -p no:cacheprovider 2>&1 | tail -3
-echo "== dist check x$N"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/dist_2gpu_check.py 2>&1 | grep -v "^W\|^\*\*\*" | tail -3
+echo "== dist kernel tests"; timeout 600 python -m pytest tests/test_dist_gpu.py -m gpu -q -x --timeout 300 -p no:cacheprovider 2>&1 | tail -12
+echo "== dist check x$N"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/dist_2gpu_check.py 2>&1 | grep -v "^W\|^\*\*\*" | tail -12
 for ex in p2p nccl; do
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 3 --exchange $ex 2>&1 | grep -v "^W\|^\*\*\*" | tail -1 | tee gpurun_out/bench_dist_${N}_$ex.json | python -c "
 import sys, json
