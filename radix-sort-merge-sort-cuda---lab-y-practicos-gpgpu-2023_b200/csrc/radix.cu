@@ -231,7 +231,10 @@ __device__ __forceinline__ void cluster_wait() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int WARPS, int IPT, int MIN_BLOCKS, int MODE, int CL>
+// PF > 0: after issuing its own loads a CTA prefetches into L2 the tile PF tickets ahead (the
+// tile some CTA will pick up about one CTA-lifetime later), so that tile's loads hit L2.
+// BSF: group B stages its keys before consuming the look-back window instead of after.
+template <int WARPS, int IPT, int MIN_BLOCKS, int MODE, int CL, int PF = 0, int BSF = 0>
 __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
 radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n, int pass,
                       RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
@@ -307,6 +310,14 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             for (int i = 0; i < IPT; ++i)
                 key[i] = (wofs + i * 32 < valid) ? ld_stream(src + i * 32) : 0x7FFFFFFF;  // sorts last
         }
+    }
+    if (PF > 0) {
+        constexpr uint32_t kLines = (uint32_t)kTile * 4 / 128;
+        const size_t ahead = ((size_t)tile + PF) * kTile + (size_t)tid * 32;
+        if (tid < kLines && ahead + 32 <= n)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(in + ahead));
+        if (kLines > (uint32_t)kThreads && tid + kThreads < kLines && ahead + (size_t)kThreads * 32 + 32 <= n)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(in + ahead + (size_t)kThreads * 32));
     }
 
     // ---- rank inside the warp: earlier keys of this warp with my digit ----------------------------
@@ -471,6 +482,19 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
         if (looker) {
             st_relaxed_gpu(const_cast<uint32_t *>(look), (link == 0 ? kFlagIncl : kFlagLocal) | total);
             if (status_next != nullptr) status_next[(size_t)link * kRadixBins + bd] = 0;
+        }
+        if (BSF && kSplit && CL == 1) {
+            // positions are final as soon as group A says so: stage my keys while the prefetched
+            // status words are still in flight
+            asm volatile("bar.sync 3, %0;" :: "n"(WARPS * 32) : "memory");
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const uint32_t d = digit_of(key[i], shift, flip);
+                const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
+                s_keys[s_table[(warp * kRadixBins + d) * TW + (TW - 1)] + r] = key[i];
+            }
+        }
+        if (looker) {
             if (link > 0) {
                 uint32_t back = 1;                           // distance of the window's first link
                 bool have = kSplit;                          // window already loaded?
@@ -512,7 +536,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             cluster_wait();
             if (!looker) prev = s_prev[bd];
         }
-        if (kSplit) asm volatile("bar.sync 3, %0;" :: "n"(WARPS * 32) : "memory");
+        if (kSplit && !(BSF && CL == 1)) asm volatile("bar.sync 3, %0;" :: "n"(WARPS * 32) : "memory");
         s_gofs[bd] = digit_base + prev + before - s_tstart[bd];
     }
     // Positions must be final before anybody stages keys: group A knows (its barrier 1), group B
@@ -521,11 +545,13 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     if (!kSplit) __syncthreads();
 
     // ---- stage the keys in shared memory in digit order ---------------------------------------------
+    if (!(BSF && kSplit && CL == 1 && in_b)) {
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        const uint32_t d = digit_of(key[i], shift, flip);
-        const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
-        s_keys[s_table[(warp * kRadixBins + d) * TW + (TW - 1)] + r] = key[i];
+        for (int i = 0; i < IPT; ++i) {
+            const uint32_t d = digit_of(key[i], shift, flip);
+            const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
+            s_keys[s_table[(warp * kRadixBins + d) * TW + (TW - 1)] + r] = key[i];
+        }
     }
     if (CL > 1 && !in_b) cluster_wait();                     // finish #2 (group B already did)
     __syncthreads();
@@ -951,6 +977,11 @@ struct Variant {
       OnesweepShape<W, I, M>::kTile, OnesweepShape<W, I, M>::kSmemBytes,                            \
       radix_onesweep_kernel<W, I, B, M, C> }
 
+#define B200_VARIANT_X(W, I, B, M, C, P, S)                                                         \
+    { "warps" #W "_ipt" #I "_occ" #B "_" #M "_cl" #C "_pf" #P "_bsf" #S, M, C, OnesweepShape<W, I, M>::kThreads, \
+      OnesweepShape<W, I, M>::kTile, OnesweepShape<W, I, M>::kSmemBytes,                            \
+      radix_onesweep_kernel<W, I, B, M, C, P, S> }
+
 #define B200_PP_VARIANT(I)                                                                          \
     { "pipelined_14w_ipt" #I "_kRankAdd", kRankAdd, 0, kPPThreads, PipelinedShape<I>::kTile,        \
       PipelinedShape<I>::kSmemBytes, radix_onesweep_pipelined_kernel<I> }
@@ -983,6 +1014,11 @@ const Variant kVariants[] = {
     B200_VARIANT(32, 8, 2, kRankAdd, 1),       // 24: 8192
     B200_VARIANT(32, 12, 1, kRankAdd, 1),      // 25: 12288, 1 CTA/SM
     B200_VARIANT(24, 12, 2, kRankAdd, 1),      // 26: 768 threads x 12 = 9216, 2 CTAs/SM (42 regs)
+    B200_VARIANT_X(16, 20, 2, kRankAdd, 1, 296, 0),   // 27: default shape + L2 prefetch one CTA-lifetime ahead
+    B200_VARIANT_X(16, 20, 2, kRankAdd, 1, 0, 1),     // 28: default shape, group B stages before the look-back
+    B200_VARIANT_X(16, 20, 2, kRankAdd, 1, 296, 1),   // 29: both
+    B200_VARIANT_X(16, 20, 2, kRankAdd, 1, 592, 1),   // 30: both, two lifetimes ahead
+    B200_VARIANT_X(16, 16, 2, kRankAdd, 1, 296, 1),   // 31: 8192-key tiles, both
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
