@@ -130,6 +130,9 @@ size_t      b200sort_radix_tile(void);            /* keys per onesweep tile of t
  * (BLOCKS on first call; needs a device) and otherwise launches the ballot-ranked shape instead.
  * Returns 1 (ordered: fast shapes in use) or 0.  B200SORT_RANK_SAFE=1 in the environment forces 0. */
 int         b200sort_radix_atomic_order_ok(void);
+/* Profiling aid: TIMING_* shapes stamp clock64() at their phase boundaries into this device buffer
+ * (grid x 2 x 10 int64); NULL switches the probe off.  tools/phase_timing.py reads it. */
+int         b200sort_debug_set_phase_buffer(void *d_buf);
 /* Name of the shape that will actually be launched (after the self-test's verdict). */
 const char *b200sort_radix_effective_variant_name(void);
 /* Pass skipping: when a digit histogram shows one bin holding every key the pass is the

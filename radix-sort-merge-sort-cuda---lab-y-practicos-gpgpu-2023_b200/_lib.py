@@ -54,6 +54,7 @@ SIGNATURES = {
     "b200sort_radix_variant_name": (ctypes.c_char_p, [_i]),
     "b200sort_radix_tile": (_sz, []),
     "b200sort_radix_set_skip": (_i, [_i]),
+    "b200sort_debug_set_phase_buffer": (_i, [_vp]),
     "b200sort_radix_atomic_order_ok": (_i, []),
     "b200sort_radix_effective_variant_name": (ctypes.c_char_p, []),
     "b200sort_launch_count": (_u64, []),

@@ -22,6 +22,7 @@ const char *radix_variant_name(int v);
 int radix_set_variant(int v);
 void radix_set_skip(int enabled);
 int radix_atomic_order_ok();
+int radix_set_phase_debug(long long *d_buf);
 const char *radix_effective_variant_name();
 
 namespace {
@@ -345,6 +346,7 @@ int b200sort_radix_set_variant(int variant) { return radix_set_variant(variant);
 int b200sort_radix_num_variants(void) { return radix_num_variants(); }
 const char *b200sort_radix_variant_name(int variant) { return radix_variant_name(variant); }
 size_t b200sort_radix_tile(void) { return radix_current_tile(); }
+int b200sort_debug_set_phase_buffer(void *d_buf) { return radix_set_phase_debug(static_cast<long long *>(d_buf)); }
 int b200sort_radix_atomic_order_ok(void) { return radix_atomic_order_ok(); }
 const char *b200sort_radix_effective_variant_name(void) { return radix_effective_variant_name(); }
 int b200sort_radix_set_skip(int enabled) { radix_set_skip(enabled); return B200SORT_OK; }

@@ -231,10 +231,19 @@ __device__ __forceinline__ void cluster_wait() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Phase-timing probe (TIMING variants only): lane 0 of warp 0 (group A) and of warp 8 (group B)
+// stamp clock64() at the phase boundaries into g_phase_dbg[tile][2][10].
+__device__ long long *g_phase_dbg = nullptr;
+#define B200_STAMP(slot)                                                                  \
+    do {                                                                                  \
+        if (TIMING && g_phase_dbg != nullptr && lane == 0 && (warp == 0 || warp == 8))    \
+            g_phase_dbg[((size_t)dbg_tile * 2 + (warp >> 3)) * 10 + (slot)] = clock64();  \
+    } while (0)
+
 // PF > 0: after issuing its own loads a CTA prefetches into L2 the tile PF tickets ahead (the
 // tile some CTA will pick up about one CTA-lifetime later), so that tile's loads hit L2.
 // BSF: group B stages its keys before consuming the look-back window instead of after.
-template <int WARPS, int IPT, int MIN_BLOCKS, int MODE, int CL, int PF = 0, int BSF = 0>
+template <int WARPS, int IPT, int MIN_BLOCKS, int MODE, int CL, int PF = 0, int BSF = 0, int TIMING = 0>
 __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
 radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n, int pass,
                       RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
@@ -255,6 +264,8 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     uint32_t *s_misc  = s_gofs + kRadixBins;                                      // [16]
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t dbg_tile = blockIdx.x;
+    B200_STAMP(0);
 
     // follow_plan: buffers and skipping come from the plan the histogram kernel wrote.
     const int32_t *in = in_buf;
@@ -291,6 +302,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     if (CL > 1) { cluster_arrive(); cluster_wait(); } else __syncthreads();
     const uint32_t link = s_misc[8];                         // my link of the look-back chain
     const uint32_t tile = link * CL + crank;
+    B200_STAMP(1);
     const size_t tile_base = (size_t)tile * kTile;
     const uint32_t valid = (tile_base >= n) ? 0u
                          : (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
@@ -320,6 +332,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             asm volatile("prefetch.global.L2 [%0];" :: "l"(in + ahead + (size_t)kThreads * 32));
     }
 
+    if (TIMING) { asm volatile("" :: "r"(key[0]), "r"(key[IPT - 1])); B200_STAMP(2); }   // loads have landed
     // ---- rank inside the warp: earlier keys of this warp with my digit ----------------------------
     // (two 16-bit ranks per register: a warp holds at most 32*IPT < 65536 keys)
     static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in pairs");
@@ -391,7 +404,9 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
         }
         }
     }
+    if (TIMING) { asm volatile("" :: "r"(rank2[0]), "r"(rank2[IPT / 2 - 1])); B200_STAMP(3); }   // ranked
     __syncthreads();
+    B200_STAMP(4);
 
     // ---- per digit, two thread groups working side by side --------------------------------------
     //   group A (threads 0..255, thread = digit): tile totals, exclusive scan over the digits,
@@ -456,6 +471,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
         if (kSplit) { __threadfence_block(); asm volatile("bar.arrive 3, %0;" :: "n"(WARPS * 32) : "memory"); }
         asm volatile("bar.sync 1, 256;" ::: "memory");      // every (warp, digit) position is final
         if (CL > 1) { cluster_wait(); cluster_arrive(); }    // finish #1; #2: nothing to announce
+        B200_STAMP(5);                                       // group A done
     }
     if (CL > 1 && !in_a && !in_b) { cluster_arrive(); cluster_wait(); cluster_arrive(); }
     if (kSplit && !in_a && !in_b) asm volatile("bar.sync 3, %0;" :: "n"(WARPS * 32) : "memory");   // warps 16..: wait for the positions
@@ -538,6 +554,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
         }
         if (kSplit && !(BSF && CL == 1)) asm volatile("bar.sync 3, %0;" :: "n"(WARPS * 32) : "memory");
         s_gofs[bd] = digit_base + prev + before - s_tstart[bd];
+        B200_STAMP(5);                                       // group B done (look-back finished)
     }
     // Positions must be final before anybody stages keys: group A knows (its barrier 1), group B
     // knows (barrier 3); a CTA that is not split simply synchronises.
@@ -554,7 +571,9 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
         }
     }
     if (CL > 1 && !in_b) cluster_wait();                     // finish #2 (group B already did)
+    B200_STAMP(6);                                           // staged
     __syncthreads();
+    B200_STAMP(7);
 
     // ---- scatter: consecutive threads write consecutive addresses inside each digit run -----------
     if (valid == (uint32_t)kTile) {
@@ -574,6 +593,9 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             }
         }
     }
+    B200_STAMP(8);
+    if (TIMING && g_phase_dbg != nullptr && lane == 0 && (warp == 0 || warp == 8))
+        g_phase_dbg[((size_t)dbg_tile * 2 + (warp >> 3)) * 10 + 9] = tile;
 }
 
 // ================================================================================================
@@ -982,6 +1004,11 @@ struct Variant {
       OnesweepShape<W, I, M>::kTile, OnesweepShape<W, I, M>::kSmemBytes,                            \
       radix_onesweep_kernel<W, I, B, M, C, P, S> }
 
+#define B200_VARIANT_T(W, I, B, M, C, P, S)                                                         \
+    { "TIMING_warps" #W "_ipt" #I "_" #M "_pf" #P, M, C, OnesweepShape<W, I, M>::kThreads,              \
+      OnesweepShape<W, I, M>::kTile, OnesweepShape<W, I, M>::kSmemBytes,                            \
+      radix_onesweep_kernel<W, I, B, M, C, P, S, 1> }
+
 #define B200_PP_VARIANT(I)                                                                          \
     { "pipelined_14w_ipt" #I "_kRankAdd", kRankAdd, 0, kPPThreads, PipelinedShape<I>::kTile,        \
       PipelinedShape<I>::kSmemBytes, radix_onesweep_pipelined_kernel<I> }
@@ -1019,6 +1046,7 @@ const Variant kVariants[] = {
     B200_VARIANT_X(16, 20, 2, kRankAdd, 1, 296, 1),   // 29: both
     B200_VARIANT_X(16, 20, 2, kRankAdd, 1, 592, 1),   // 30: both, two lifetimes ahead
     B200_VARIANT_X(16, 16, 2, kRankAdd, 1, 296, 1),   // 31: 8192-key tiles, both
+    B200_VARIANT_T(16, 20, 2, kRankAdd, 1, 296, 0),   // 32: variant 27 with the phase-timing probe
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
@@ -1122,6 +1150,10 @@ int effective_variant() {
 }
 }  // namespace
 
+int radix_set_phase_debug(long long *d_buf) {
+    B200_CUDA_TRY(cudaMemcpyToSymbol(g_phase_dbg, &d_buf, sizeof d_buf));
+    return B200SORT_OK;
+}
 int radix_atomic_order_ok() { return atomic_order_ok(); }
 int radix_num_variants() { return kNumVariants; }
 const char *radix_variant_name(int v) { return (v >= 0 && v < kNumVariants) ? kVariants[v].name : nullptr; }
