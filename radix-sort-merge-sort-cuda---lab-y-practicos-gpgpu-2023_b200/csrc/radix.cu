@@ -220,6 +220,45 @@ __device__ __forceinline__ uint32_t digit_of(int32_t key, int shift, uint32_t fl
     return ((static_cast<uint32_t>(key) >> shift) & (kRadixBins - 1)) ^ flip;
 }
 
+// ---- two-level look-back ---------------------------------------------------------------------------
+// Measured with the phase probe (tools/phase_timing.py): with one level the look-back takes 4.7 us of
+// a 9 us tile lifetime.  The inclusive front can only advance (window / L2 round trip) = 8 / 0.26 us
+// = 31 tiles per microsecond, which is exactly the rate the pass ran at: the chain, not the SMs,
+// set the speed.  With two levels tiles are grouped kLookGroup at a time and a tile's prefix is
+//   (totals of the earlier GROUPS) + (totals of the earlier tiles of ITS group);
+// both are walks over rows whose partial values (a tile's own total, a group's own total) do not
+// depend on any other walk, so nobody waits for a long serial chain.
+constexpr int kLookGroup = 32;
+
+// Walk back over status rows for one digit: the row at distance d (1 <= d <= max_dist) is
+// first - (d-1)*256.  Flags: 0 not published (poll again), kFlagLocal partial (keep walking),
+// kFlagIncl inclusive (stop).  Rows beyond max_dist count as inclusive zero.
+template <int W>
+__device__ __forceinline__ uint32_t walk_back(const uint32_t *first, uint32_t max_dist) {
+    uint32_t acc = 0, back = 1;
+    for (;;) {
+        uint32_t win[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            win[j] = (back + j <= max_dist) ? ld_relaxed_gpu(first - (size_t)(back + j - 1) * kRadixBins) : kFlagIncl;
+        bool done = false;
+        uint32_t used = 0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            if (!done && used == (uint32_t)j) {
+                const uint32_t f = win[j] & ~kValueMask;
+                if (f != 0) {
+                    acc += win[j] & kValueMask;
+                    used = j + 1;
+                    done = (f == kFlagIncl);
+                }
+            }
+        }
+        if (done) return acc;
+        back += used;
+    }
+}
+
 // CL > 1: the CTAs of a thread-block cluster take CL consecutive tiles and act as ONE link of the
 // look-back chain: tile totals are exchanged through distributed shared memory, the last CTA of
 // the cluster publishes / looks back for all of them and hands the result to its peers.  The
@@ -243,7 +282,8 @@ __device__ long long *g_phase_dbg = nullptr;
 // PF > 0: after issuing its own loads a CTA prefetches into L2 the tile PF tickets ahead (the
 // tile some CTA will pick up about one CTA-lifetime later), so that tile's loads hit L2.
 // BSF: group B stages its keys before consuming the look-back window instead of after.
-template <int WARPS, int IPT, int MIN_BLOCKS, int MODE, int CL, int PF = 0, int BSF = 0, int TIMING = 0>
+// TL: two-level look-back (tile rows + group rows, see walk_back below); implies BSF.
+template <int WARPS, int IPT, int MIN_BLOCKS, int MODE, int CL, int PF = 0, int BSF = 0, int TIMING = 0, int TL = 0>
 __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
 radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n, int pass,
                       RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
@@ -275,6 +315,8 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             // Identity pass.  Still hand the next pass a clean status buffer.
             if (status_next != nullptr && tid < kRadixBins && blockIdx.x % CL == 0)
                 status_next[(size_t)(blockIdx.x / CL) * kRadixBins + tid] = 0;
+            if (TL && status_next != nullptr && tid < kRadixBins && blockIdx.x % kLookGroup == 0)
+                status_next[((n + kTile - 1) / kTile + blockIdx.x / kLookGroup) * kRadixBins + tid] = 0;
             return;
         }
         const uint32_t ss = ctl->src_sel[pass], ds = ctl->dst_sel[pass];
@@ -433,7 +475,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     uint32_t win[kLookWindow];
     uint32_t digit_base = 0;                                 // global start of my digit (group B)
     if (in_b) digit_base = ctl->base[pass][bd];              // fetched early: it is off the critical path
-    if (kSplit && in_b && looker) {
+    if (kSplit && in_b && looker && !TL) {
         // first window, issued before anything else so that it overlaps group A's work
 #pragma unroll
         for (int j = 0; j < kLookWindow; ++j)
@@ -495,11 +537,46 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             if (looker) total += rest;
         }
         uint32_t prev = 0;
-        if (looker) {
+        if (TL) {
+            static_assert(!TL || (CL == 1 && WARPS >= 16), "two-level look-back: split CTAs without clusters");
+            const size_t num_tiles = (n + kTile - 1) / kTile;
+            const uint32_t group = tile / kLookGroup, r = tile % kLookGroup;
+            const bool last_of_group = (r == kLookGroup - 1) || ((size_t)tile + 1 == num_tiles);
+            uint32_t *row = status_cur + (size_t)tile * kRadixBins + bd;                   // tile rows ...
+            uint32_t *grow = status_cur + (num_tiles + group) * kRadixBins + bd;           // ... then group rows
+            st_relaxed_gpu(row, (r == 0 ? kFlagIncl : kFlagLocal) | total);               // inclusive WITHIN the group
+            if (status_next != nullptr) {
+                status_next[(size_t)tile * kRadixBins + bd] = 0;
+                if (last_of_group) status_next[(num_tiles + group) * kRadixBins + bd] = 0;
+            }
+            // stage my keys now (positions are final once group A says so): that frees their
+            // registers for the windows below and overlaps with the predecessors' publishing
+            asm volatile("bar.sync 3, %0;" :: "n"(WARPS * 32) : "memory");
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const uint32_t d = digit_of(key[i], shift, flip);
+                const uint32_t rk = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
+                s_keys[s_table[(warp * kRadixBins + d) * TW + (TW - 1)] + rk] = key[i];
+            }
+            uint32_t inprev = 0;
+            if (r > 0) {
+                inprev = walk_back<16>(row - kRadixBins, r);
+                st_relaxed_gpu(row, kFlagIncl | (inprev + total));
+            }
+            const uint32_t gtot = inprev + total;
+            if (last_of_group) st_relaxed_gpu(grow, (group == 0 ? kFlagIncl : kFlagLocal) | gtot);
+            uint32_t gprev = 0;
+            if (group > 0) {
+                gprev = walk_back<16>(grow - kRadixBins, group);
+                if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + gtot) & kValueMask));
+            }
+            prev = inprev + gprev;
+        }
+        if (!TL && looker) {
             st_relaxed_gpu(const_cast<uint32_t *>(look), (link == 0 ? kFlagIncl : kFlagLocal) | total);
             if (status_next != nullptr) status_next[(size_t)link * kRadixBins + bd] = 0;
         }
-        if (BSF && kSplit && CL == 1) {
+        if (!TL && BSF && kSplit && CL == 1) {
             // positions are final as soon as group A says so: stage my keys while the prefetched
             // status words are still in flight
             asm volatile("bar.sync 3, %0;" :: "n"(WARPS * 32) : "memory");
@@ -510,7 +587,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
                 s_keys[s_table[(warp * kRadixBins + d) * TW + (TW - 1)] + r] = key[i];
             }
         }
-        if (looker) {
+        if (!TL && looker) {
             if (link > 0) {
                 uint32_t back = 1;                           // distance of the window's first link
                 bool have = kSplit;                          // window already loaded?
@@ -552,7 +629,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
             cluster_wait();
             if (!looker) prev = s_prev[bd];
         }
-        if (kSplit && !(BSF && CL == 1)) asm volatile("bar.sync 3, %0;" :: "n"(WARPS * 32) : "memory");
+        if (kSplit && !((BSF || TL) && CL == 1)) asm volatile("bar.sync 3, %0;" :: "n"(WARPS * 32) : "memory");
         s_gofs[bd] = digit_base + prev + before - s_tstart[bd];
         B200_STAMP(5);                                       // group B done (look-back finished)
     }
@@ -562,7 +639,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     if (!kSplit) __syncthreads();
 
     // ---- stage the keys in shared memory in digit order ---------------------------------------------
-    if (!(BSF && kSplit && CL == 1 && in_b)) {
+    if (!((BSF || TL) && kSplit && CL == 1 && in_b)) {
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const uint32_t d = digit_of(key[i], shift, flip);
@@ -640,7 +717,7 @@ __device__ __forceinline__ void st_relaxed_gpu_v4(uint32_t *p, uint4 v) {
 // front only has to advance one GROUP per round trip.  (With one level the front must advance one
 // tile per round trip times the window, which is what bounded the pass: ~35 tiles start per
 // microsecond and a status round trip through L2 takes ~0.4 us.)
-constexpr int kPPGroup = 32;
+constexpr int kPPGroup = kLookGroup;
 
 // Walk back over status rows: row at distance d (1 <= d <= max_dist) is `first - (d-1)*256`; each
 // thread handles four digits with 128-bit loads, W rows in flight.  Flags: 0 not published yet
@@ -988,6 +1065,7 @@ struct Variant {
     const char *name;
     int mode;
     int cluster;       // CTAs per cluster (1 = none); 0 marks the persistent pipelined kernel
+    int two_level;     // status rows: one per tile plus one per group of kLookGroup tiles
     int threads;
     int tile;
     size_t smem;
@@ -995,22 +1073,27 @@ struct Variant {
 };
 
 #define B200_VARIANT(W, I, B, M, C)                                                                 \
-    { "warps" #W "_ipt" #I "_occ" #B "_" #M "_cl" #C, M, C, OnesweepShape<W, I, M>::kThreads,         \
+    { "warps" #W "_ipt" #I "_occ" #B "_" #M "_cl" #C, M, C, 0, OnesweepShape<W, I, M>::kThreads,      \
       OnesweepShape<W, I, M>::kTile, OnesweepShape<W, I, M>::kSmemBytes,                            \
       radix_onesweep_kernel<W, I, B, M, C> }
 
 #define B200_VARIANT_X(W, I, B, M, C, P, S)                                                         \
-    { "warps" #W "_ipt" #I "_occ" #B "_" #M "_cl" #C "_pf" #P "_bsf" #S, M, C, OnesweepShape<W, I, M>::kThreads, \
+    { "warps" #W "_ipt" #I "_occ" #B "_" #M "_cl" #C "_pf" #P "_bsf" #S, M, C, 0, OnesweepShape<W, I, M>::kThreads, \
       OnesweepShape<W, I, M>::kTile, OnesweepShape<W, I, M>::kSmemBytes,                            \
       radix_onesweep_kernel<W, I, B, M, C, P, S> }
 
-#define B200_VARIANT_T(W, I, B, M, C, P, S)                                                         \
-    { "TIMING_warps" #W "_ipt" #I "_" #M "_pf" #P, M, C, OnesweepShape<W, I, M>::kThreads,              \
+#define B200_VARIANT_T(W, I, B, M, C, P, S, L)                                                       \
+    { "TIMING_warps" #W "_ipt" #I "_" #M "_pf" #P "_tl" #L, M, C, L, OnesweepShape<W, I, M>::kThreads,  \
       OnesweepShape<W, I, M>::kTile, OnesweepShape<W, I, M>::kSmemBytes,                            \
-      radix_onesweep_kernel<W, I, B, M, C, P, S, 1> }
+      radix_onesweep_kernel<W, I, B, M, C, P, S, 1, L> }
+
+#define B200_VARIANT_TL(W, I, B, M, P)                                                              \
+    { "warps" #W "_ipt" #I "_occ" #B "_" #M "_pf" #P "_twolevel", M, 1, 1, OnesweepShape<W, I, M>::kThreads, \
+      OnesweepShape<W, I, M>::kTile, OnesweepShape<W, I, M>::kSmemBytes,                            \
+      radix_onesweep_kernel<W, I, B, M, 1, P, 1, 0, 1> }
 
 #define B200_PP_VARIANT(I)                                                                          \
-    { "pipelined_14w_ipt" #I "_kRankAdd", kRankAdd, 0, kPPThreads, PipelinedShape<I>::kTile,        \
+    { "pipelined_14w_ipt" #I "_kRankAdd", kRankAdd, 0, 1, kPPThreads, PipelinedShape<I>::kTile,     \
       PipelinedShape<I>::kSmemBytes, radix_onesweep_pipelined_kernel<I> }
 
 const Variant kVariants[] = {
@@ -1046,7 +1129,14 @@ const Variant kVariants[] = {
     B200_VARIANT_X(16, 20, 2, kRankAdd, 1, 296, 1),   // 29: both
     B200_VARIANT_X(16, 20, 2, kRankAdd, 1, 592, 1),   // 30: both, two lifetimes ahead
     B200_VARIANT_X(16, 16, 2, kRankAdd, 1, 296, 1),   // 31: 8192-key tiles, both
-    B200_VARIANT_T(16, 20, 2, kRankAdd, 1, 296, 0),   // 32: variant 27 with the phase-timing probe
+    B200_VARIANT_T(16, 20, 2, kRankAdd, 1, 296, 0, 0),   // 32: variant 27 with the phase-timing probe
+    B200_VARIANT_TL(16, 20, 2, kRankAdd, 296),        // 33: two-level look-back, 10240-key tiles
+    B200_VARIANT_TL(16, 20, 2, kRankAdd, 0),          // 34: same without the L2 prefetch
+    B200_VARIANT_TL(16, 16, 2, kRankAdd, 296),        // 35: 8192
+    B200_VARIANT_TL(16, 18, 2, kRankAdd, 296),        // 36: 9216
+    B200_VARIANT_TL(16, 22, 2, kRankAdd, 296),        // 37: 11264
+    B200_VARIANT_TL(16, 24, 2, kRankAdd, 296),        // 38: 12288
+    B200_VARIANT_T(16, 20, 2, kRankAdd, 1, 296, 1, 1),   // 39: variant 33 with the phase-timing probe
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
@@ -1099,7 +1189,7 @@ int ensure_hist_attr() {
 
 // status rows a pass needs: one per tile, plus (pipelined kernel) one per group of tiles
 size_t status_rows(const Variant &var, size_t tiles) {
-    return var.cluster == 0 ? tiles + div_up(tiles, (size_t)kPPGroup) : tiles;
+    return var.two_level ? tiles + div_up(tiles, (size_t)kLookGroup) : tiles;
 }
 
 int launch_onesweep(const Variant &var, size_t tiles, cudaStream_t s, const int32_t *in, int32_t *out,
