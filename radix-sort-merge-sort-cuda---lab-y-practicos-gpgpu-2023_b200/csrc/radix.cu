@@ -271,12 +271,12 @@ __device__ __forceinline__ void cluster_wait() {
 }
 
 // Phase-timing probe (TIMING variants only): lane 0 of warp 0 (group A) and of warp 8 (group B)
-// stamp clock64() at the phase boundaries into g_phase_dbg[tile][2][10].
+// stamp clock64() at the phase boundaries into g_phase_dbg[tile][2][16].
 __device__ long long *g_phase_dbg = nullptr;
 #define B200_STAMP(slot)                                                                  \
     do {                                                                                  \
         if (TIMING && g_phase_dbg != nullptr && lane == 0 && (warp == 0 || warp == 8))    \
-            g_phase_dbg[((size_t)dbg_tile * 2 + (warp >> 3)) * 10 + (slot)] = clock64();  \
+            g_phase_dbg[((size_t)dbg_tile * 2 + (warp >> 3)) * 16 + (slot)] = clock64();  \
     } while (0)
 
 // PF > 0: after issuing its own loads a CTA prefetches into L2 the tile PF tickets ahead (the
@@ -558,11 +558,13 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
                 const uint32_t rk = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
                 s_keys[s_table[(warp * kRadixBins + d) * TW + (TW - 1)] + rk] = key[i];
             }
+            B200_STAMP(10);                                  // staged, walks start
             uint32_t inprev = 0;
             if (r > 0) {
                 inprev = walk_back<16>(row - kRadixBins, r);
                 st_relaxed_gpu(row, kFlagIncl | (inprev + total));
             }
+            B200_STAMP(11);                                  // level 1 done
             const uint32_t gtot = inprev + total;
             if (last_of_group) st_relaxed_gpu(grow, (group == 0 ? kFlagIncl : kFlagLocal) | gtot);
             uint32_t gprev = 0;
@@ -571,6 +573,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
                 if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + gtot) & kValueMask));
             }
             prev = inprev + gprev;
+            B200_STAMP(12);                                  // level 2 done
         }
         if (!TL && looker) {
             st_relaxed_gpu(const_cast<uint32_t *>(look), (link == 0 ? kFlagIncl : kFlagLocal) | total);
@@ -672,7 +675,7 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
     }
     B200_STAMP(8);
     if (TIMING && g_phase_dbg != nullptr && lane == 0 && (warp == 0 || warp == 8))
-        g_phase_dbg[((size_t)dbg_tile * 2 + (warp >> 3)) * 10 + 9] = tile;
+        g_phase_dbg[((size_t)dbg_tile * 2 + (warp >> 3)) * 16 + 9] = tile;
 }
 
 // ================================================================================================
