@@ -1005,6 +1005,271 @@ radix_onesweep_pipelined_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t
     }
 }
 
+// ================================================================================================
+// k2'': persistent CTA, every warp a worker, DELAYED two-level look-back
+// ================================================================================================
+// What the phase probe showed (profiles/r01_phase_timing.txt): a tile needs the counts of the tiles
+// that started a few hundred nanoseconds before it, and those are often not published yet --
+// the look-back does not wait for a long chain but for STRAGGLERS among its ~32 nearest
+// predecessors, 4-5 us of a 9 us tile lifetime, with the SM's registers and shared memory held idle.
+// Here the CTA does not wait: it publishes tile i's counts, then ranks and stages tile i+1, and only
+// then resolves tile i's prefix -- by which time every straggler has long published -- and writes
+// tile i out.  The two-level rows make that possible: a tile's own total and a group's own total do
+// not depend on anybody's look-back, so delaying one's OWN prefix delays nobody else.  Only the last
+// tile of each group sums its group right away (1 tile in 32 waits for stragglers).
+//   tile row  : kFlagLocal = the tile's digit counts, kFlagIncl = inclusive within its group
+//   group row : kFlagLocal = the group's digit counts, kFlagIncl = inclusive over all groups
+template <int IPT>
+struct Pipelined2Shape {
+    static constexpr int kThreads = 512;
+    static constexpr int kTile = kThreads * IPT;
+    static constexpr size_t kSmemBytes =
+        (size_t)16 * kRadixBins * 4                 // per-warp digit counters -> positions
+        + (size_t)2 * kTile * 4                     // two staging buffers
+        + (size_t)(2 + 1 + 2) * kRadixBins * 4      // gofs[2], total, tstart[2]
+        + 128;
+};
+
+template <int IPT>
+__global__ void __launch_bounds__(512, 2)
+radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
+                                 int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
+                                 int follow_plan)
+{
+    constexpr int kThreads = 512, kWarps = 16;
+    constexpr int kTile = Pipelined2Shape<IPT>::kTile;
+    constexpr int W = 8;                                      // status rows in flight per thread
+    static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in pairs");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *s_table  = reinterpret_cast<uint32_t *>(smem_raw);                      // [16][256]
+    int32_t  *s_keys   = reinterpret_cast<int32_t *>(s_table + kWarps * kRadixBins);  // [2][kTile]
+    uint32_t *s_gofs   = reinterpret_cast<uint32_t *>(s_keys + 2 * kTile);            // [2][256]
+    uint32_t *s_total  = s_gofs + 2 * kRadixBins;                                     // [256]
+    uint32_t *s_tstart = s_total + kRadixBins;                                        // [2][256]
+    uint32_t *s_misc   = s_tstart + 2 * kRadixBins;        // [0..7] warp sums, [8..9] tickets
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t tiles = (n + kTile - 1) / kTile;
+
+    const int32_t *in = in_buf;
+    int32_t *out = out_buf;
+    if (follow_plan) {
+        if (ctl->skip[pass]) {
+            const size_t rows = tiles + (tiles + kLookGroup - 1) / kLookGroup;
+            if (status_next != nullptr)
+                for (size_t row = blockIdx.x; row < rows; row += gridDim.x)
+                    if (tid < kRadixBins) status_next[row * kRadixBins + tid] = 0;
+            return;
+        }
+        const uint32_t ss = ctl->src_sel[pass], ds = ctl->dst_sel[pass];
+        in = (ss == kSelIn) ? in_buf : (ss == kSelTmp) ? tmp_buf : out_buf;
+        out = (ds == kSelTmp) ? tmp_buf : out_buf;
+    }
+    const int shift = pass * kRadixBits;
+    const uint32_t flip = (pass == kRadixPasses - 1) ? 0x80u : 0u;
+    const uint32_t lt = lanemask_lt();
+    const bool in_a = tid < kRadixBins;                       // warps 0..7 : thread = digit
+    const bool in_b = !in_a;                                  // warps 8..15: thread - 256 = digit
+    const uint32_t bd = tid - kRadixBins;
+    uint32_t *wt = s_table + warp * kRadixBins;
+    const uint32_t wofs = warp * (32 * IPT) + lane;
+
+    int32_t key[IPT];
+    auto load_tile = [&](uint32_t t) {
+        const size_t tile_base = (size_t)t * kTile;
+        const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
+        const int32_t *src = in + tile_base + wofs;
+        if (valid == (uint32_t)kTile) {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) key[i] = ld_stream(src + i * 32);
+        } else {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i)
+                key[i] = (wofs + i * 32 < valid) ? ld_stream(src + i * 32) : 0x7FFFFFFF;
+        }
+    };
+    auto write_tile = [&](uint32_t t, int buf) {
+        const size_t tile_base = (size_t)t * kTile;
+        const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
+        const int32_t *sk = s_keys + buf * kTile;
+        const uint32_t *go = s_gofs + buf * kRadixBins;
+        if (valid == (uint32_t)kTile) {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const uint32_t p = tid + j * kThreads;
+                const int32_t k = sk[p];
+                st_stream(out + (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p), k);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const uint32_t p = tid + j * kThreads;
+                if (p < valid) {
+                    const int32_t k = sk[p];
+                    st_stream(out + (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p), k);
+                }
+            }
+        }
+    };
+
+    // group B's memory of the previous tile (the one whose prefix is resolved one iteration late)
+    uint32_t digit_base = in_b ? ctl->base[pass][bd] : 0u;
+    uint32_t p_total = 0, p_in = 0;                           // its count of my digit; in-group prefix if known
+    bool p_in_known = false;
+    // The previous tile's look-back, run by group B: fills s_gofs[buf].
+    auto resolve_prev = [&](uint32_t pt, int buf) {
+        const uint32_t group = pt / kLookGroup, r = pt % kLookGroup;
+        const bool last_of_group = (r == kLookGroup - 1) || ((size_t)pt + 1 == tiles);
+        uint32_t *row = status_cur + (size_t)pt * kRadixBins + bd;
+        uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
+        uint32_t inprev = p_in;
+        if (!p_in_known) {
+            inprev = (r > 0) ? walk_back<W>(row - kRadixBins, r) : 0u;
+            if (r > 0) st_relaxed_gpu(row, kFlagIncl | (inprev + p_total));   // shortens later walks
+        }
+        uint32_t gprev = 0;
+        if (group > 0) {
+            gprev = walk_back<W>(grow - kRadixBins, group);
+            if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + inprev + p_total) & kValueMask));
+        }
+        s_gofs[buf * kRadixBins + bd] = digit_base + inprev + gprev - s_tstart[buf * kRadixBins + bd];
+    };
+
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(wt);
+#pragma unroll
+        for (int j = lane; j < kRadixBins / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
+    __syncthreads();
+    uint32_t tile = s_misc[8];
+    uint32_t prev_tile = 0xFFFFFFFFu;
+    if (tile < tiles) load_tile(tile);
+    int b = 0;
+    uint32_t iter = 0;
+
+    while (tile < tiles) {
+        // ---- rank: one shared-memory atomicAdd per key (lane-ordered; see the self-test) ----------
+        uint32_t rank2[IPT / 2];
+        {
+            const uint32_t d0 = digit_of(key[0], shift, flip);
+            const uint32_t agree = __ballot_sync(0xffffffffu, d0 == __shfl_sync(0xffffffffu, d0, 0));
+            const bool hot = (follow_plan && ctl->hot[pass] != 0) || __popc(agree) >= 8;
+            if (!hot) {
+#pragma unroll
+                for (int i = 0; i < IPT; ++i) {
+                    const uint32_t r = atomicAdd(wt + digit_of(key[i], shift, flip), 1u);
+                    rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < IPT; ++i) {
+                    const uint32_t d = digit_of(key[i], shift, flip);
+                    const bool same = (d == __shfl_sync(0xffffffffu, d, 0));
+                    const uint32_t sm = __ballot_sync(0xffffffffu, same);
+                    uint32_t r = 0;
+                    if (!same || lane == 0) r = atomicAdd(wt + d, lane == 0 ? (uint32_t)__popc(sm) : 1u);
+                    const uint32_t r0 = __shfl_sync(0xffffffffu, r, 0);
+                    if (same) r = r0 + __popc(sm & lt);
+                    rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
+                }
+            }
+        }
+        __syncthreads();                                      // SYNC1: counts are final
+        if (tid == 0) s_misc[8 + ((iter + 1) & 1)] = atomicAdd(&ctl->ticket[pass], 1u);
+
+        if (in_a) {
+            // thread = digit: tile totals -> group B; exclusive scan; warp counts -> positions
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) total += s_table[w * kRadixBins + tid];
+            s_total[tid] = total;
+            __threadfence_block();
+            bar_arrive(2, 512);
+            uint32_t x = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= (uint32_t)o) x += y;
+            }
+            if (lane == 31) s_misc[warp] = x;
+            bar_sync(1, kRadixBins);
+            uint32_t add = 0;
+#pragma unroll
+            for (int w = 0; w < kRadixBins / 32; ++w) add += (w < (int)warp) ? s_misc[w] : 0u;
+            const uint32_t tile_start = x - total + add;
+            uint32_t run = tile_start;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const uint32_t c = s_table[w * kRadixBins + tid];
+                s_table[w * kRadixBins + tid] = run;
+                run += c;
+            }
+            s_tstart[b * kRadixBins + tid] = tile_start;
+        } else {
+            // publish this tile's counts at once ...
+            bar_sync(2, 512);
+            const uint32_t total = s_total[bd];
+            const uint32_t group = tile / kLookGroup, r = tile % kLookGroup;
+            const bool last_of_group = (r == kLookGroup - 1) || ((size_t)tile + 1 == tiles);
+            uint32_t *row = status_cur + (size_t)tile * kRadixBins + bd;
+            st_relaxed_gpu(row, (r == 0 ? kFlagIncl : kFlagLocal) | total);
+            if (status_next != nullptr) {
+                status_next[(size_t)tile * kRadixBins + bd] = 0;
+                if (last_of_group) status_next[(tiles + group) * kRadixBins + bd] = 0;
+            }
+            // ... resolve the PREVIOUS tile's prefix (everything it needs was published long ago) ...
+            if (prev_tile != 0xFFFFFFFFu) resolve_prev(prev_tile, b ^ 1);
+            // ... and, for the last tile of a group only, sum the group now so that nobody after
+            // it has to wait an iteration for the group's total
+            p_total = total;
+            p_in_known = false;
+            if (last_of_group) {
+                p_in = (r > 0) ? walk_back<W>(row - kRadixBins, r) : 0u;
+                p_in_known = true;
+                if (r > 0) st_relaxed_gpu(row, kFlagIncl | (p_in + total));
+                uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
+                st_relaxed_gpu(grow, (group == 0 ? kFlagIncl : kFlagLocal) | (p_in + total));
+            }
+            __syncwarp();
+        }
+        __syncthreads();                                      // SYNC2: positions final, previous tile's offsets ready
+        const uint32_t next = s_misc[8 + ((iter + 1) & 1)];
+
+        // ---- stage this tile's keys in digit order ----------------------------------------------------
+        {
+            int32_t *sk = s_keys + b * kTile;
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
+                sk[wt[digit_of(key[i], shift, flip)] + r] = key[i];
+            }
+        }
+        __syncwarp();
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(wt);          // my warp's counters, for the next tile
+#pragma unroll
+            for (int j = lane; j < kRadixBins / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+        // ---- the next tile's loads go out now and land while the previous tile is written --------
+        if (next < tiles) load_tile(next);
+        if (prev_tile != 0xFFFFFFFFu) write_tile(prev_tile, b ^ 1);
+        prev_tile = tile;
+        tile = next;
+        b ^= 1;
+        ++iter;
+    }
+    // ---- drain: the last tile is staged, its prefix is still to be resolved ----------------------------
+    if (prev_tile != 0xFFFFFFFFu) {
+        __syncthreads();
+        if (in_b) resolve_prev(prev_tile, b ^ 1);
+        __syncthreads();
+        write_tile(prev_tile, b ^ 1);
+    }
+}
+
 // The plan's final copy (only ever needed with pass skipping): tmp -> out when an in-place sort
 // executed an odd number of passes, in -> out when an out-of-place sort executed none.
 __global__ void __launch_bounds__(256)
@@ -1099,6 +1364,10 @@ struct Variant {
     { "pipelined_14w_ipt" #I "_kRankAdd", kRankAdd, 0, 1, kPPThreads, PipelinedShape<I>::kTile,     \
       PipelinedShape<I>::kSmemBytes, radix_onesweep_pipelined_kernel<I> }
 
+#define B200_PP2_VARIANT(I)                                                                         \
+    { "pipelined2_16w_ipt" #I "_kRankAdd_delayed_twolevel", kRankAdd, 0, 1, 512,                    \
+      Pipelined2Shape<I>::kTile, Pipelined2Shape<I>::kSmemBytes, radix_onesweep_pipelined2_kernel<I> }
+
 const Variant kVariants[] = {
     B200_VARIANT(16, 20, 2, kRankAdd, 1),      //  0: 10240-key tiles, 2 CTAs/SM  (default; fastest measured)
     B200_VARIANT(16, 18, 2, kRankAdd, 1),      //  1: 9216
@@ -1140,6 +1409,10 @@ const Variant kVariants[] = {
     B200_VARIANT_TL(16, 22, 2, kRankAdd, 296),        // 37: 11264
     B200_VARIANT_TL(16, 24, 2, kRankAdd, 296),        // 38: 12288
     B200_VARIANT_T(16, 20, 2, kRankAdd, 1, 296, 1, 1),   // 39: variant 33 with the phase-timing probe
+    B200_PP2_VARIANT(20),                             // 40: persistent, delayed two-level look-back, 10240
+    B200_PP2_VARIANT(16),                             // 41: 8192
+    B200_PP2_VARIANT(18),                             // 42: 9216
+    B200_PP2_VARIANT(22),                             // 43: 11264
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
