@@ -1030,7 +1030,7 @@ struct Pipelined2Shape {
         + 128;
 };
 
-template <int IPT>
+template <int IPT, int TIMING = 0>
 __global__ void __launch_bounds__(512, 2)
 radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                  int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
@@ -1150,6 +1150,9 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
     uint32_t iter = 0;
 
     while (tile < tiles) {
+        const uint32_t dbg_tile = tile;
+        if (TIMING) { asm volatile("" :: "r"(key[0]), "r"(key[IPT - 1])); }
+        B200_STAMP(0);                                        // this tile's keys are in registers
         // ---- rank: one shared-memory atomicAdd per key (lane-ordered; see the self-test) ----------
         uint32_t rank2[IPT / 2];
         {
@@ -1176,7 +1179,10 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
                 }
             }
         }
+        if (TIMING) { asm volatile("" :: "r"(rank2[0]), "r"(rank2[IPT / 2 - 1])); }
+        B200_STAMP(1);                                        // ranked
         __syncthreads();                                      // SYNC1: counts are final
+        B200_STAMP(2);
         if (tid == 0) s_misc[8 + ((iter + 1) & 1)] = atomicAdd(&ctl->ticket[pass], 1u);
 
         if (in_a) {
@@ -1207,6 +1213,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
                 run += c;
             }
             s_tstart[b * kRadixBins + tid] = tile_start;
+            B200_STAMP(3);                                    // group A done
         } else {
             // publish this tile's counts at once ...
             bar_sync(2, 512);
@@ -1219,8 +1226,10 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
                 status_next[(size_t)tile * kRadixBins + bd] = 0;
                 if (last_of_group) status_next[(tiles + group) * kRadixBins + bd] = 0;
             }
+            B200_STAMP(10);                                   // published
             // ... resolve the PREVIOUS tile's prefix (everything it needs was published long ago) ...
             if (prev_tile != 0xFFFFFFFFu) resolve_prev(prev_tile, b ^ 1);
+            B200_STAMP(11);                                   // previous tile resolved
             // ... and, for the last tile of a group only, sum the group now so that nobody after
             // it has to wait an iteration for the group's total
             p_total = total;
@@ -1233,8 +1242,10 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
                 st_relaxed_gpu(grow, (group == 0 ? kFlagIncl : kFlagLocal) | (p_in + total));
             }
             __syncwarp();
+            B200_STAMP(3);                                    // group B done
         }
         __syncthreads();                                      // SYNC2: positions final, previous tile's offsets ready
+        B200_STAMP(4);
         const uint32_t next = s_misc[8 + ((iter + 1) & 1)];
 
         // ---- stage this tile's keys in digit order ----------------------------------------------------
@@ -1253,9 +1264,14 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
             for (int j = lane; j < kRadixBins / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
         }
         __syncwarp();
+        B200_STAMP(5);                                        // staged
         // ---- the next tile's loads go out now and land while the previous tile is written --------
         if (next < tiles) load_tile(next);
+        B200_STAMP(6);
         if (prev_tile != 0xFFFFFFFFu) write_tile(prev_tile, b ^ 1);
+        B200_STAMP(7);                                        // previous tile written
+        if (TIMING && g_phase_dbg != nullptr && lane == 0 && (warp == 0 || warp == 8))
+            g_phase_dbg[((size_t)dbg_tile * 2 + (warp >> 3)) * 16 + 9] = tile;
         prev_tile = tile;
         tile = next;
         b ^= 1;
@@ -1413,6 +1429,8 @@ const Variant kVariants[] = {
     B200_PP2_VARIANT(16),                             // 41: 8192
     B200_PP2_VARIANT(18),                             // 42: 9216
     B200_PP2_VARIANT(22),                             // 43: 11264
+    { "TIMING_pipelined2_ipt18", kRankAdd, 0, 1, 512, Pipelined2Shape<18>::kTile,
+      Pipelined2Shape<18>::kSmemBytes, radix_onesweep_pipelined2_kernel<18, 1> },   // 44
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
