@@ -1030,7 +1030,18 @@ struct Pipelined2Shape {
         + 128;
 };
 
-template <int IPT, int TIMING = 0>
+// LEVELS == 3: tiles are grouped 8 at a time (g1) and g1 groups 8 at a time (g2 = 64 tiles).  A tile's
+// prefix is  (tiles before it in its g1 group) + (g1 groups before its own in its g2 group) +
+// (g2 groups before its own).  Each term is at most one window of 8 status rows, the three windows
+// are independent and are loaded TOGETHER, so resolving a prefix costs about one L2 round trip
+// (the probe measured ~4000 cycles for the two sequential walks of the two-level scheme).
+// Every row is published by a delayed, non-blocking resolve: the last tile of a g1 / g2 group
+// publishes the group's total when it resolves its own prefix.
+//   tile row: kFlagLocal | count      g1 row: kFlagLocal | total of its 8 tiles
+//   g2 row  : kFlagLocal | total of its 64 tiles, then kFlagIncl | inclusive over all g2 groups
+constexpr int kG1 = 8, kG2 = 64;
+
+template <int IPT, int TIMING = 0, int LEVELS = 2>
 __global__ void __launch_bounds__(512, 2)
 radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                  int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
@@ -1056,7 +1067,8 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
     int32_t *out = out_buf;
     if (follow_plan) {
         if (ctl->skip[pass]) {
-            const size_t rows = tiles + (tiles + kLookGroup - 1) / kLookGroup;
+            const size_t rows = (LEVELS == 3) ? tiles + (tiles + kG1 - 1) / kG1 + (tiles + kG2 - 1) / kG2
+                                              : tiles + (tiles + kLookGroup - 1) / kLookGroup;
             if (status_next != nullptr)
                 for (size_t row = blockIdx.x; row < rows; row += gridDim.x)
                     if (tid < kRadixBins) status_next[row * kRadixBins + tid] = 0;
@@ -1118,7 +1130,78 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
     uint32_t p_total = 0, p_in = 0;                           // its count of my digit; in-group prefix if known
     bool p_in_known = false;
     // The previous tile's look-back, run by group B: fills s_gofs[buf].
+    const size_t n1 = (tiles + kG1 - 1) / kG1;                // g1 rows follow the tile rows, g2 rows follow them
+    auto resolve_prev3 = [&](uint32_t pt, int buf) {
+        const uint32_t r1 = pt % kG1, g1 = pt / kG1, r2 = g1 % (kG2 / kG1), g2 = pt / kG2;
+        const bool last1 = (r1 == kG1 - 1) || ((size_t)pt + 1 == tiles);
+        const bool last2 = (last1 && r2 == kG2 / kG1 - 1) || ((size_t)pt + 1 == tiles);
+        const uint32_t *row  = status_cur + (size_t)pt * kRadixBins + bd;
+        uint32_t *row1 = status_cur + (tiles + g1) * kRadixBins + bd;
+        uint32_t *row2 = status_cur + (tiles + n1 + g2) * kRadixBins + bd;
+        uint32_t w1[kG1 - 1], w2[kG2 / kG1 - 1], w3[8];
+        // all three windows go out together
+#pragma unroll
+        for (int j = 0; j < kG1 - 1; ++j) w1[j] = ((uint32_t)j < r1) ? ld_relaxed_gpu(row - (size_t)(j + 1) * kRadixBins) : kFlagLocal;
+#pragma unroll
+        for (int j = 0; j < kG2 / kG1 - 1; ++j) w2[j] = ((uint32_t)j < r2) ? ld_relaxed_gpu(row1 - (size_t)(j + 1) * kRadixBins) : kFlagLocal;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w3[j] = ((uint32_t)j < g2) ? ld_relaxed_gpu(row2 - (size_t)(j + 1) * kRadixBins) : kFlagIncl;
+        // level 1 and 2: every row in the window must be there
+        uint32_t in1 = 0, in2 = 0;
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < kG1 - 1; ++j) ok = ok && ((w1[j] & ~kValueMask) != 0);
+            if (ok) break;
+#pragma unroll
+            for (int j = 0; j < kG1 - 1; ++j)
+                if ((uint32_t)j < r1 && (w1[j] & ~kValueMask) == 0) w1[j] = ld_relaxed_gpu(row - (size_t)(j + 1) * kRadixBins);
+        }
+#pragma unroll
+        for (int j = 0; j < kG1 - 1; ++j) in1 += w1[j] & kValueMask;
+        if (last1) st_relaxed_gpu(row1, kFlagLocal | (in1 + p_total));
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < kG2 / kG1 - 1; ++j) ok = ok && ((w2[j] & ~kValueMask) != 0);
+            if (ok) break;
+#pragma unroll
+            for (int j = 0; j < kG2 / kG1 - 1; ++j)
+                if ((uint32_t)j < r2 && (w2[j] & ~kValueMask) == 0) w2[j] = ld_relaxed_gpu(row1 - (size_t)(j + 1) * kRadixBins);
+        }
+#pragma unroll
+        for (int j = 0; j < kG2 / kG1 - 1; ++j) in2 += w2[j] & kValueMask;
+        if (last2) st_relaxed_gpu(row2, (g2 == 0 ? kFlagIncl : kFlagLocal) | (in2 + in1 + p_total));
+        // level 3: walk the g2 rows back to an inclusive one (first window already loaded)
+        uint32_t in3 = 0;
+        if (g2 > 0) {
+            uint32_t back = 1;
+            bool have = true;
+            for (;;) {
+                if (!have) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        w3[j] = (back + j <= g2) ? ld_relaxed_gpu(row2 - (size_t)(back + j) * kRadixBins) : kFlagIncl;
+                }
+                have = false;
+                bool done = false;
+                uint32_t used = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (!done && used == (uint32_t)j) {
+                        const uint32_t f = w3[j] & ~kValueMask;
+                        if (f != 0) { in3 += w3[j] & kValueMask; used = j + 1; done = (f == kFlagIncl); }
+                    }
+                }
+                if (done) break;
+                back += used;
+            }
+            if (last2) st_relaxed_gpu(row2, kFlagIncl | ((in3 + in2 + in1 + p_total) & kValueMask));
+        }
+        s_gofs[buf * kRadixBins + bd] = digit_base + in1 + in2 + in3 - s_tstart[buf * kRadixBins + bd];
+    };
     auto resolve_prev = [&](uint32_t pt, int buf) {
+        if (LEVELS == 3) { resolve_prev3(pt, buf); return; }
         const uint32_t group = pt / kLookGroup, r = pt % kLookGroup;
         const bool last_of_group = (r == kLookGroup - 1) || ((size_t)pt + 1 == tiles);
         uint32_t *row = status_cur + (size_t)pt * kRadixBins + bd;
@@ -1219,12 +1302,18 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
             bar_sync(2, 512);
             const uint32_t total = s_total[bd];
             const uint32_t group = tile / kLookGroup, r = tile % kLookGroup;
-            const bool last_of_group = (r == kLookGroup - 1) || ((size_t)tile + 1 == tiles);
+            const bool last_of_group = (LEVELS == 2) && ((r == kLookGroup - 1) || ((size_t)tile + 1 == tiles));
             uint32_t *row = status_cur + (size_t)tile * kRadixBins + bd;
-            st_relaxed_gpu(row, (r == 0 ? kFlagIncl : kFlagLocal) | total);
+            st_relaxed_gpu(row, ((LEVELS == 2 && r == 0) ? kFlagIncl : kFlagLocal) | total);
             if (status_next != nullptr) {
                 status_next[(size_t)tile * kRadixBins + bd] = 0;
-                if (last_of_group) status_next[(tiles + group) * kRadixBins + bd] = 0;
+                if (LEVELS == 2) {
+                    if (last_of_group) status_next[(tiles + group) * kRadixBins + bd] = 0;
+                } else {
+                    const bool end = ((size_t)tile + 1 == tiles);
+                    if (tile % kG1 == kG1 - 1 || end) status_next[(tiles + tile / kG1) * kRadixBins + bd] = 0;
+                    if (tile % kG2 == kG2 - 1 || end) status_next[(tiles + n1 + tile / kG2) * kRadixBins + bd] = 0;
+                }
             }
             B200_STAMP(10);                                   // published
             // ... resolve the PREVIOUS tile's prefix (everything it needs was published long ago) ...
@@ -1349,7 +1438,8 @@ struct Variant {
     const char *name;
     int mode;
     int cluster;       // CTAs per cluster (1 = none); 0 marks the persistent pipelined kernel
-    int two_level;     // status rows: one per tile plus one per group of kLookGroup tiles
+    int two_level;     // status rows: 0 one per tile; 1 plus one per group of kLookGroup tiles;
+                       // 3 plus one per 8 tiles plus one per 64 tiles
     int threads;
     int tile;
     size_t smem;
@@ -1383,6 +1473,10 @@ struct Variant {
 #define B200_PP2_VARIANT(I)                                                                         \
     { "pipelined2_16w_ipt" #I "_kRankAdd_delayed_twolevel", kRankAdd, 0, 1, 512,                    \
       Pipelined2Shape<I>::kTile, Pipelined2Shape<I>::kSmemBytes, radix_onesweep_pipelined2_kernel<I> }
+
+#define B200_PP3_VARIANT(I)                                                                         \
+    { "pipelined3_16w_ipt" #I "_kRankAdd_delayed_threelevel", kRankAdd, 0, 3, 512,                  \
+      Pipelined2Shape<I>::kTile, Pipelined2Shape<I>::kSmemBytes, radix_onesweep_pipelined2_kernel<I, 0, 3> }
 
 const Variant kVariants[] = {
     B200_VARIANT(16, 20, 2, kRankAdd, 1),      //  0: 10240-key tiles, 2 CTAs/SM  (default; fastest measured)
@@ -1431,6 +1525,11 @@ const Variant kVariants[] = {
     B200_PP2_VARIANT(22),                             // 43: 11264
     { "TIMING_pipelined2_ipt18", kRankAdd, 0, 1, 512, Pipelined2Shape<18>::kTile,
       Pipelined2Shape<18>::kSmemBytes, radix_onesweep_pipelined2_kernel<18, 1> },   // 44
+    B200_PP3_VARIANT(18),                             // 45: three-level, windows loaded together
+    B200_PP3_VARIANT(16),                             // 46
+    B200_PP3_VARIANT(20),                             // 47
+    { "TIMING_pipelined2_threelevel_ipt18", kRankAdd, 0, 3, 512, Pipelined2Shape<18>::kTile,
+      Pipelined2Shape<18>::kSmemBytes, radix_onesweep_pipelined2_kernel<18, 1, 3> },   // 48
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
@@ -1483,6 +1582,7 @@ int ensure_hist_attr() {
 
 // status rows a pass needs: one per tile, plus (pipelined kernel) one per group of tiles
 size_t status_rows(const Variant &var, size_t tiles) {
+    if (var.two_level == 3) return tiles + div_up(tiles, (size_t)kG1) + div_up(tiles, (size_t)kG2);
     return var.two_level ? tiles + div_up(tiles, (size_t)kLookGroup) : tiles;
 }
 
@@ -1552,7 +1652,7 @@ const char *radix_effective_variant_name() { return kVariants[effective_variant(
 
 size_t radix_workspace_bytes(size_t n) {
     const size_t tiles = div_up(n > 0 ? n : 1, kRadixMinTile);
-    const size_t rows = tiles + div_up(tiles, (size_t)kPPGroup) + 1;
+    const size_t rows = tiles + div_up(tiles, (size_t)kG1) + div_up(tiles, (size_t)kG2) + 2;
     return kRadixControlBytes + 2 * rows * kRadixBins * sizeof(uint32_t);
 }
 
