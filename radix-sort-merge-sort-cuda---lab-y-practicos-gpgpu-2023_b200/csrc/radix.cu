@@ -259,42 +259,6 @@ __device__ __forceinline__ uint32_t walk_back(const uint32_t *first, uint32_t ma
     }
 }
 
-// The same walk when the first window (distances 1..W) was loaded earlier by window_load.
-template <int W>
-__device__ __forceinline__ void window_load(const uint32_t *first, uint32_t max_dist, uint32_t (&win)[W]) {
-#pragma unroll
-    for (int j = 0; j < W; ++j)
-        win[j] = ((uint32_t)(j + 1) <= max_dist) ? ld_relaxed_gpu(first - (size_t)j * kRadixBins) : kFlagIncl;
-}
-template <int W>
-__device__ __forceinline__ uint32_t walk_back_preloaded(const uint32_t *first, uint32_t max_dist, uint32_t (&win)[W]) {
-    uint32_t acc = 0, back = 1;
-    bool have = true;
-    for (;;) {
-        if (!have) {
-#pragma unroll
-            for (int j = 0; j < W; ++j)
-                win[j] = (back + j <= max_dist) ? ld_relaxed_gpu(first - (size_t)(back + j - 1) * kRadixBins) : kFlagIncl;
-        }
-        have = false;
-        bool done = false;
-        uint32_t used = 0;
-#pragma unroll
-        for (int j = 0; j < W; ++j) {
-            if (!done && used == (uint32_t)j) {
-                const uint32_t f = win[j] & ~kValueMask;
-                if (f != 0) {
-                    acc += win[j] & kValueMask;
-                    used = j + 1;
-                    done = (f == kFlagIncl);
-                }
-            }
-        }
-        if (done) return acc;
-        back += used;
-    }
-}
-
 // CL > 1: the CTAs of a thread-block cluster take CL consecutive tiles and act as ONE link of the
 // look-back chain: tile totals are exchanged through distributed shared memory, the last CTA of
 // the cluster publishes / looks back for all of them and hands the result to its peers.  The
@@ -1163,8 +1127,8 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
 
     // group B's memory of the previous tile (the one whose prefix is resolved one iteration late)
     uint32_t digit_base = in_b ? ctl->base[pass][bd] : 0u;
-    uint32_t p_total = 0, p_in = 0, p_g = 0;                  // its count of my digit; its two prefixes if known
-    bool p_in_known = false;                                  // (known = it was the last tile of its group)
+    uint32_t p_total = 0, p_in = 0;                           // its count of my digit; in-group prefix if known
+    bool p_in_known = false;
     // The previous tile's look-back, run by group B: fills s_gofs[buf].
     const size_t n1 = (tiles + kG1 - 1) / kG1;                // g1 rows follow the tile rows, g2 rows follow them
     auto resolve_prev3 = [&](uint32_t pt, int buf) {
@@ -1236,28 +1200,21 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
         }
         s_gofs[buf * kRadixBins + bd] = digit_base + in1 + in2 + in3 - s_tstart[buf * kRadixBins + bd];
     };
-    // The previous tile's look-back, run by group B in two steps: the first windows of both walks
-    // are LOADED right after SYNC1 (they fly while group A sums the counts), and CONSUMED after this
-    // tile's counts have been published.  Fills s_gofs[buf].
-    uint32_t w1[W], w2[W];
-    auto resolve_prev_load = [&](uint32_t pt) {
-        if (LEVELS == 3) return;
-        const uint32_t group = pt / kLookGroup, r = pt % kLookGroup;
-        if (!p_in_known) {
-            window_load<W>(status_cur + (size_t)pt * kRadixBins + bd - kRadixBins, r, w1);
-            window_load<W>(status_cur + (tiles + group) * kRadixBins + bd - kRadixBins, group, w2);
-        }
-    };
     auto resolve_prev = [&](uint32_t pt, int buf) {
         if (LEVELS == 3) { resolve_prev3(pt, buf); return; }
         const uint32_t group = pt / kLookGroup, r = pt % kLookGroup;
+        const bool last_of_group = (r == kLookGroup - 1) || ((size_t)pt + 1 == tiles);
         uint32_t *row = status_cur + (size_t)pt * kRadixBins + bd;
         uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
-        uint32_t inprev = p_in, gprev = p_g;
-        if (!p_in_known) {        // (the last tile of a group resolved both prefixes when it published)
-            inprev = (r > 0) ? walk_back_preloaded<W>(row - kRadixBins, r, w1) : 0u;
+        uint32_t inprev = p_in;
+        if (!p_in_known) {
+            inprev = (r > 0) ? walk_back<W>(row - kRadixBins, r) : 0u;
             if (r > 0) st_relaxed_gpu(row, kFlagIncl | (inprev + p_total));   // shortens later walks
-            gprev = (group > 0) ? walk_back_preloaded<W>(grow - kRadixBins, group, w2) : 0u;
+        }
+        uint32_t gprev = 0;
+        if (group > 0) {
+            gprev = walk_back<W>(grow - kRadixBins, group);
+            if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + inprev + p_total) & kValueMask));
         }
         s_gofs[buf * kRadixBins + bd] = digit_base + inprev + gprev - s_tstart[buf * kRadixBins + bd];
     };
@@ -1341,9 +1298,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
             s_tstart[b * kRadixBins + tid] = tile_start;
             B200_STAMP(3);                                    // group A done
         } else {
-            // the previous tile's status windows go out first ...
-            if (prev_tile != 0xFFFFFFFFu) resolve_prev_load(prev_tile);
-            // ... then publish this tile's counts as soon as group A has them ...
+            // publish this tile's counts at once ...
             bar_sync(2, 512);
             const uint32_t total = s_total[bd];
             const uint32_t group = tile / kLookGroup, r = tile % kLookGroup;
@@ -1374,13 +1329,6 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
                 if (r > 0) st_relaxed_gpu(row, kFlagIncl | (p_in + total));
                 uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
                 st_relaxed_gpu(grow, (group == 0 ? kFlagIncl : kFlagLocal) | (p_in + total));
-                // and make the group row inclusive right away: everybody's second walk then ends
-                // after a row or two
-                p_g = 0;
-                if (group > 0) {
-                    p_g = walk_back<W>(grow - kRadixBins, group);
-                    st_relaxed_gpu(grow, kFlagIncl | ((p_g + p_in + total) & kValueMask));
-                }
             }
             __syncwarp();
             B200_STAMP(3);                                    // group B done
@@ -1421,7 +1369,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
     // ---- drain: the last tile is staged, its prefix is still to be resolved ----------------------------
     if (prev_tile != 0xFFFFFFFFu) {
         __syncthreads();
-        if (in_b) { resolve_prev_load(prev_tile); resolve_prev(prev_tile, b ^ 1); }
+        if (in_b) resolve_prev(prev_tile, b ^ 1);
         __syncthreads();
         write_tile(prev_tile, b ^ 1);
     }
