@@ -1049,7 +1049,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
 {
     constexpr int kThreads = 512, kWarps = 16;
     constexpr int kTile = Pipelined2Shape<IPT>::kTile;
-    constexpr int W = 8;                                      // status rows in flight per thread
+    constexpr int W = (LEVELS == 2) ? 16 : 8;                 // status rows in flight per thread
     static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in pairs");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1296,7 +1296,10 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
                 run += c;
             }
             s_tstart[b * kRadixBins + tid] = tile_start;
-            B200_STAMP(3);                                    // group A done
+            __threadfence_block();
+            bar_arrive(3, 512);                               // tell group B; then wait for the rest of group A
+            bar_sync(1, kRadixBins);
+            B200_STAMP(3);                                    // group A done: positions are final
         } else {
             // publish this tile's counts at once ...
             bar_sync(2, 512);
@@ -1331,9 +1334,11 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
                 st_relaxed_gpu(grow, (group == 0 ? kFlagIncl : kFlagLocal) | (p_in + total));
             }
             __syncwarp();
+            bar_sync(3, 512);                                 // positions are final
             B200_STAMP(3);                                    // group B done
         }
-        __syncthreads();                                      // SYNC2: positions final, previous tile's offsets ready
+        // Nobody waits for the other group here: each stages its keys as soon as the positions are
+        // final; the previous tile's offsets (group B's look-back) are only needed for the write below.
         B200_STAMP(4);
         const uint32_t next = s_misc[8 + ((iter + 1) & 1)];
 
@@ -1357,6 +1362,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
         // ---- the next tile's loads go out now and land while the previous tile is written --------
         if (next < tiles) load_tile(next);
         B200_STAMP(6);
+        __syncthreads();                                      // SYNC2: previous tile's offsets ready (and this tile staged)
         if (prev_tile != 0xFFFFFFFFu) write_tile(prev_tile, b ^ 1);
         B200_STAMP(7);                                        // previous tile written
         if (TIMING && g_phase_dbg != nullptr && lane == 0 && (warp == 0 || warp == 8))

@@ -6,7 +6,8 @@ import numpy as np, torch
 from b200sort._lib import lib, check, ALGO_RADIX
 L = lib()
 n = 1 << 28
-v = [i for i in range(L.b200sort_radix_num_variants()) if L.b200sort_radix_variant_name(i).startswith(b"TIMING_pipelined2")][-1]
+want = sys.argv[1].encode() if len(sys.argv) > 1 else b"TIMING_pipelined2_ipt"
+v = [i for i in range(L.b200sort_radix_num_variants()) if L.b200sort_radix_variant_name(i).startswith(want)][-1]
 print("shape:", L.b200sort_radix_variant_name(v).decode())
 check(L.b200sort_radix_set_variant(v))
 tile = L.b200sort_radix_tile(); tiles = (n + tile - 1) // tile
