@@ -230,6 +230,31 @@ __device__ __forceinline__ uint32_t digit_of(int32_t key, int shift, uint32_t fl
 // depend on any other walk, so nobody waits for a long serial chain.
 constexpr int kLookGroup = 32;
 
+// Consume one window of status words (win[0] is the nearest row): add up the published words up to
+// and including the first inclusive one; *taken = how many were consumed; returns true when an
+// inclusive word ended the walk.  Branch-free on purpose: the straightforward "for each entry, if
+// still going ..." loop is a chain of ~8 dependent instructions per entry, and the phase probe
+// showed that chain -- not the L2 round trip -- to be most of the look-back time.
+template <int W>
+__device__ __forceinline__ bool window_take(const uint32_t (&win)[W], uint32_t *acc, uint32_t *taken) {
+    uint32_t pub = 0, inc = 0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const uint32_t f = win[j] >> 30;                     // 0 not published, 1 partial, 2 inclusive
+        pub |= (f != 0 ? 1u : 0u) << j;
+        inc |= (f >> 1) << j;
+    }
+    const uint32_t first_unpub = __ffs(~pub) - 1;            // <= W: bits W.. of pub are clear
+    const uint32_t first_inc = inc ? (uint32_t)__ffs(inc) - 1 : 32u;
+    const uint32_t take = first_unpub < first_inc + 1 ? first_unpub : first_inc + 1;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) sum += ((uint32_t)j < take) ? (win[j] & kValueMask) : 0u;
+    *acc += sum;
+    *taken = take;
+    return first_inc < first_unpub;
+}
+
 // Walk back over status rows for one digit: the row at distance d (1 <= d <= max_dist) is
 // first - (d-1)*256.  Flags: 0 not published (poll again), kFlagLocal partial (keep walking),
 // kFlagIncl inclusive (stop).  Rows beyond max_dist count as inclusive zero.
@@ -241,20 +266,8 @@ __device__ __forceinline__ uint32_t walk_back(const uint32_t *first, uint32_t ma
 #pragma unroll
         for (int j = 0; j < W; ++j)
             win[j] = (back + j <= max_dist) ? ld_relaxed_gpu(first - (size_t)(back + j - 1) * kRadixBins) : kFlagIncl;
-        bool done = false;
-        uint32_t used = 0;
-#pragma unroll
-        for (int j = 0; j < W; ++j) {
-            if (!done && used == (uint32_t)j) {
-                const uint32_t f = win[j] & ~kValueMask;
-                if (f != 0) {
-                    acc += win[j] & kValueMask;
-                    used = j + 1;
-                    done = (f == kFlagIncl);
-                }
-            }
-        }
-        if (done) return acc;
+        uint32_t used;
+        if (window_take<W>(win, &acc, &used)) return acc;
         back += used;
     }
 }
@@ -602,20 +615,8 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
                                                         : kFlagIncl;
                     }
                     have = false;
-                    bool done = false;
-                    uint32_t used = 0;
-#pragma unroll
-                    for (int j = 0; j < kLookWindow; ++j) {
-                        if (!done && used == (uint32_t)j) {
-                            const uint32_t f = win[j] & ~kValueMask;
-                            if (f != 0) {                    // published: take it
-                                prev += win[j] & kValueMask;
-                                used = j + 1;
-                                done = (f == kFlagIncl);
-                            }
-                        }
-                    }
-                    if (done) break;
+                    uint32_t used;
+                    if (window_take<kLookWindow>(win, &prev, &used)) break;
                     back += used;                            // re-poll from the first unpublished link
                 }
                 st_relaxed_gpu(const_cast<uint32_t *>(look), kFlagIncl | ((prev + total) & kValueMask));
