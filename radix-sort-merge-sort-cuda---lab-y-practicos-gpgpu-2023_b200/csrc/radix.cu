@@ -259,9 +259,10 @@ __device__ __forceinline__ bool window_take(const uint32_t (&win)[W], uint32_t *
 // first - (d-1)*256.  Flags: 0 not published (poll again), kFlagLocal partial (keep walking),
 // kFlagIncl inclusive (stop).  Rows beyond max_dist count as inclusive zero.
 template <int W>
-__device__ __forceinline__ uint32_t walk_back(const uint32_t *first, uint32_t max_dist) {
+__device__ __forceinline__ uint32_t walk_back(const uint32_t *first, uint32_t max_dist, uint32_t *windows = nullptr) {
     uint32_t acc = 0, back = 1;
     for (;;) {
+        if (windows) ++*windows;
         uint32_t win[W];
 #pragma unroll
         for (int j = 0; j < W; ++j)
@@ -1208,14 +1209,19 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
         uint32_t *row = status_cur + (size_t)pt * kRadixBins + bd;
         uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
         uint32_t inprev = p_in;
+        uint32_t nw1 = 0, nw2 = 0;
         if (!p_in_known) {
-            inprev = (r > 0) ? walk_back<W>(row - kRadixBins, r) : 0u;
+            inprev = (r > 0) ? walk_back<W>(row - kRadixBins, r, TIMING ? &nw1 : nullptr) : 0u;
             if (r > 0) st_relaxed_gpu(row, kFlagIncl | (inprev + p_total));   // shortens later walks
         }
         uint32_t gprev = 0;
         if (group > 0) {
-            gprev = walk_back<W>(grow - kRadixBins, group);
+            gprev = walk_back<W>(grow - kRadixBins, group, TIMING ? &nw2 : nullptr);
             if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + inprev + p_total) & kValueMask));
+        }
+        if (TIMING && g_phase_dbg != nullptr && lane == 0 && warp == 8) {
+            g_phase_dbg[((size_t)pt * 2 + 1) * 16 + 13] = nw1;
+            g_phase_dbg[((size_t)pt * 2 + 1) * 16 + 14] = nw2;
         }
         s_gofs[buf * kRadixBins + bd] = digit_base + inprev + gprev - s_tstart[buf * kRadixBins + bd];
     };

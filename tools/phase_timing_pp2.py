@@ -39,3 +39,7 @@ print("group B detail")
 for a, b2, label in ((2, 10, "SYNC1 -> counts published (waits for group A's totals)"), (10, 11, "resolve previous tile (two walks)"), (11, 3, "immediate group sum (last tile of a group only)")):
     dt = mid[:, 1, b2] - mid[:, 1, a]
     print(f"  {label:<60s} mean {dt.mean():8.0f} cyc   p50 {np.median(dt):8.0f}   p90 {np.percentile(dt, 90):8.0f}   max {dt.max():8.0f}")
+w1 = mid[:, 1, 13]; w2 = mid[:, 1, 14]
+print(f"windows loaded per resolve (digit 0 only): level 1 mean {w1.mean():.2f} max {w1.max():.0f}; level 2 mean {w2.mean():.2f} max {w2.max():.0f}")
+print("level-1 windows histogram:", np.bincount(w1.astype(int))[:12].tolist())
+print("level-2 windows histogram:", np.bincount(w2.astype(int))[:12].tolist())
