@@ -230,45 +230,31 @@ __device__ __forceinline__ uint32_t digit_of(int32_t key, int shift, uint32_t fl
 // depend on any other walk, so nobody waits for a long serial chain.
 constexpr int kLookGroup = 32;
 
-// Consume one window of status words (win[0] is the nearest row): add up the published words up to
-// and including the first inclusive one; *taken = how many were consumed; returns true when an
-// inclusive word ended the walk.  Branch-free on purpose: the straightforward "for each entry, if
-// still going ..." loop is a chain of ~8 dependent instructions per entry, and the phase probe
-// showed that chain -- not the L2 round trip -- to be most of the look-back time.
-template <int W>
-__device__ __forceinline__ bool window_take(const uint32_t (&win)[W], uint32_t *acc, uint32_t *taken) {
-    uint32_t pub = 0, inc = 0;
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-        const uint32_t f = win[j] >> 30;                     // 0 not published, 1 partial, 2 inclusive
-        pub |= (f != 0 ? 1u : 0u) << j;
-        inc |= (f >> 1) << j;
-    }
-    const uint32_t first_unpub = __ffs(~pub) - 1;            // <= W: bits W.. of pub are clear
-    const uint32_t first_inc = inc ? (uint32_t)__ffs(inc) - 1 : 32u;
-    const uint32_t take = first_unpub < first_inc + 1 ? first_unpub : first_inc + 1;
-    uint32_t sum = 0;
-#pragma unroll
-    for (int j = 0; j < W; ++j) sum += ((uint32_t)j < take) ? (win[j] & kValueMask) : 0u;
-    *acc += sum;
-    *taken = take;
-    return first_inc < first_unpub;
-}
-
 // Walk back over status rows for one digit: the row at distance d (1 <= d <= max_dist) is
 // first - (d-1)*256.  Flags: 0 not published (poll again), kFlagLocal partial (keep walking),
 // kFlagIncl inclusive (stop).  Rows beyond max_dist count as inclusive zero.
 template <int W>
-__device__ __forceinline__ uint32_t walk_back(const uint32_t *first, uint32_t max_dist, uint32_t *windows = nullptr) {
+__device__ __forceinline__ uint32_t walk_back(const uint32_t *first, uint32_t max_dist) {
     uint32_t acc = 0, back = 1;
     for (;;) {
-        if (windows) ++*windows;
         uint32_t win[W];
 #pragma unroll
         for (int j = 0; j < W; ++j)
             win[j] = (back + j <= max_dist) ? ld_relaxed_gpu(first - (size_t)(back + j - 1) * kRadixBins) : kFlagIncl;
-        uint32_t used;
-        if (window_take<W>(win, &acc, &used)) return acc;
+        bool done = false;
+        uint32_t used = 0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            if (!done && used == (uint32_t)j) {
+                const uint32_t f = win[j] & ~kValueMask;
+                if (f != 0) {
+                    acc += win[j] & kValueMask;
+                    used = j + 1;
+                    done = (f == kFlagIncl);
+                }
+            }
+        }
+        if (done) return acc;
         back += used;
     }
 }
@@ -616,8 +602,20 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
                                                         : kFlagIncl;
                     }
                     have = false;
-                    uint32_t used;
-                    if (window_take<kLookWindow>(win, &prev, &used)) break;
+                    bool done = false;
+                    uint32_t used = 0;
+#pragma unroll
+                    for (int j = 0; j < kLookWindow; ++j) {
+                        if (!done && used == (uint32_t)j) {
+                            const uint32_t f = win[j] & ~kValueMask;
+                            if (f != 0) {                    // published: take it
+                                prev += win[j] & kValueMask;
+                                used = j + 1;
+                                done = (f == kFlagIncl);
+                            }
+                        }
+                    }
+                    if (done) break;
                     back += used;                            // re-poll from the first unpublished link
                 }
                 st_relaxed_gpu(const_cast<uint32_t *>(look), kFlagIncl | ((prev + total) & kValueMask));
@@ -1032,18 +1030,7 @@ struct Pipelined2Shape {
         + 128;
 };
 
-// LEVELS == 3: tiles are grouped 8 at a time (g1) and g1 groups 8 at a time (g2 = 64 tiles).  A tile's
-// prefix is  (tiles before it in its g1 group) + (g1 groups before its own in its g2 group) +
-// (g2 groups before its own).  Each term is at most one window of 8 status rows, the three windows
-// are independent and are loaded TOGETHER, so resolving a prefix costs about one L2 round trip
-// (the probe measured ~4000 cycles for the two sequential walks of the two-level scheme).
-// Every row is published by a delayed, non-blocking resolve: the last tile of a g1 / g2 group
-// publishes the group's total when it resolves its own prefix.
-//   tile row: kFlagLocal | count      g1 row: kFlagLocal | total of its 8 tiles
-//   g2 row  : kFlagLocal | total of its 64 tiles, then kFlagIncl | inclusive over all g2 groups
-constexpr int kG1 = 8, kG2 = 64;
-
-template <int IPT, int TIMING = 0, int LEVELS = 2>
+template <int IPT, int TIMING = 0>
 __global__ void __launch_bounds__(512, 2)
 radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                  int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
@@ -1051,7 +1038,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
 {
     constexpr int kThreads = 512, kWarps = 16;
     constexpr int kTile = Pipelined2Shape<IPT>::kTile;
-    constexpr int W = (LEVELS == 2) ? 16 : 8;                 // status rows in flight per thread
+    constexpr int W = 8;                                      // status rows in flight per thread
     static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in pairs");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1069,8 +1056,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
     int32_t *out = out_buf;
     if (follow_plan) {
         if (ctl->skip[pass]) {
-            const size_t rows = (LEVELS == 3) ? tiles + (tiles + kG1 - 1) / kG1 + (tiles + kG2 - 1) / kG2
-                                              : tiles + (tiles + kLookGroup - 1) / kLookGroup;
+            const size_t rows = tiles + (tiles + kLookGroup - 1) / kLookGroup;
             if (status_next != nullptr)
                 for (size_t row = blockIdx.x; row < rows; row += gridDim.x)
                     if (tid < kRadixBins) status_next[row * kRadixBins + tid] = 0;
@@ -1132,96 +1118,20 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
     uint32_t p_total = 0, p_in = 0;                           // its count of my digit; in-group prefix if known
     bool p_in_known = false;
     // The previous tile's look-back, run by group B: fills s_gofs[buf].
-    const size_t n1 = (tiles + kG1 - 1) / kG1;                // g1 rows follow the tile rows, g2 rows follow them
-    auto resolve_prev3 = [&](uint32_t pt, int buf) {
-        const uint32_t r1 = pt % kG1, g1 = pt / kG1, r2 = g1 % (kG2 / kG1), g2 = pt / kG2;
-        const bool last1 = (r1 == kG1 - 1) || ((size_t)pt + 1 == tiles);
-        const bool last2 = (last1 && r2 == kG2 / kG1 - 1) || ((size_t)pt + 1 == tiles);
-        const uint32_t *row  = status_cur + (size_t)pt * kRadixBins + bd;
-        uint32_t *row1 = status_cur + (tiles + g1) * kRadixBins + bd;
-        uint32_t *row2 = status_cur + (tiles + n1 + g2) * kRadixBins + bd;
-        uint32_t w1[kG1 - 1], w2[kG2 / kG1 - 1], w3[8];
-        // all three windows go out together
-#pragma unroll
-        for (int j = 0; j < kG1 - 1; ++j) w1[j] = ((uint32_t)j < r1) ? ld_relaxed_gpu(row - (size_t)(j + 1) * kRadixBins) : kFlagLocal;
-#pragma unroll
-        for (int j = 0; j < kG2 / kG1 - 1; ++j) w2[j] = ((uint32_t)j < r2) ? ld_relaxed_gpu(row1 - (size_t)(j + 1) * kRadixBins) : kFlagLocal;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) w3[j] = ((uint32_t)j < g2) ? ld_relaxed_gpu(row2 - (size_t)(j + 1) * kRadixBins) : kFlagIncl;
-        // level 1 and 2: every row in the window must be there
-        uint32_t in1 = 0, in2 = 0;
-        for (;;) {
-            bool ok = true;
-#pragma unroll
-            for (int j = 0; j < kG1 - 1; ++j) ok = ok && ((w1[j] & ~kValueMask) != 0);
-            if (ok) break;
-#pragma unroll
-            for (int j = 0; j < kG1 - 1; ++j)
-                if ((uint32_t)j < r1 && (w1[j] & ~kValueMask) == 0) w1[j] = ld_relaxed_gpu(row - (size_t)(j + 1) * kRadixBins);
-        }
-#pragma unroll
-        for (int j = 0; j < kG1 - 1; ++j) in1 += w1[j] & kValueMask;
-        if (last1) st_relaxed_gpu(row1, kFlagLocal | (in1 + p_total));
-        for (;;) {
-            bool ok = true;
-#pragma unroll
-            for (int j = 0; j < kG2 / kG1 - 1; ++j) ok = ok && ((w2[j] & ~kValueMask) != 0);
-            if (ok) break;
-#pragma unroll
-            for (int j = 0; j < kG2 / kG1 - 1; ++j)
-                if ((uint32_t)j < r2 && (w2[j] & ~kValueMask) == 0) w2[j] = ld_relaxed_gpu(row1 - (size_t)(j + 1) * kRadixBins);
-        }
-#pragma unroll
-        for (int j = 0; j < kG2 / kG1 - 1; ++j) in2 += w2[j] & kValueMask;
-        if (last2) st_relaxed_gpu(row2, (g2 == 0 ? kFlagIncl : kFlagLocal) | (in2 + in1 + p_total));
-        // level 3: walk the g2 rows back to an inclusive one (first window already loaded)
-        uint32_t in3 = 0;
-        if (g2 > 0) {
-            uint32_t back = 1;
-            bool have = true;
-            for (;;) {
-                if (!have) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        w3[j] = (back + j <= g2) ? ld_relaxed_gpu(row2 - (size_t)(back + j) * kRadixBins) : kFlagIncl;
-                }
-                have = false;
-                bool done = false;
-                uint32_t used = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (!done && used == (uint32_t)j) {
-                        const uint32_t f = w3[j] & ~kValueMask;
-                        if (f != 0) { in3 += w3[j] & kValueMask; used = j + 1; done = (f == kFlagIncl); }
-                    }
-                }
-                if (done) break;
-                back += used;
-            }
-            if (last2) st_relaxed_gpu(row2, kFlagIncl | ((in3 + in2 + in1 + p_total) & kValueMask));
-        }
-        s_gofs[buf * kRadixBins + bd] = digit_base + in1 + in2 + in3 - s_tstart[buf * kRadixBins + bd];
-    };
     auto resolve_prev = [&](uint32_t pt, int buf) {
-        if (LEVELS == 3) { resolve_prev3(pt, buf); return; }
         const uint32_t group = pt / kLookGroup, r = pt % kLookGroup;
         const bool last_of_group = (r == kLookGroup - 1) || ((size_t)pt + 1 == tiles);
         uint32_t *row = status_cur + (size_t)pt * kRadixBins + bd;
         uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
         uint32_t inprev = p_in;
-        uint32_t nw1 = 0, nw2 = 0;
         if (!p_in_known) {
-            inprev = (r > 0) ? walk_back<W>(row - kRadixBins, r, TIMING ? &nw1 : nullptr) : 0u;
+            inprev = (r > 0) ? walk_back<W>(row - kRadixBins, r) : 0u;
             if (r > 0) st_relaxed_gpu(row, kFlagIncl | (inprev + p_total));   // shortens later walks
         }
         uint32_t gprev = 0;
         if (group > 0) {
-            gprev = walk_back<W>(grow - kRadixBins, group, TIMING ? &nw2 : nullptr);
+            gprev = walk_back<W>(grow - kRadixBins, group);
             if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + inprev + p_total) & kValueMask));
-        }
-        if (TIMING && g_phase_dbg != nullptr && lane == 0 && warp == 8) {
-            g_phase_dbg[((size_t)pt * 2 + 1) * 16 + 13] = nw1;
-            g_phase_dbg[((size_t)pt * 2 + 1) * 16 + 14] = nw2;
         }
         s_gofs[buf * kRadixBins + bd] = digit_base + inprev + gprev - s_tstart[buf * kRadixBins + bd];
     };
@@ -1303,27 +1213,18 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
                 run += c;
             }
             s_tstart[b * kRadixBins + tid] = tile_start;
-            __threadfence_block();
-            bar_arrive(3, 512);                               // tell group B; then wait for the rest of group A
-            bar_sync(1, kRadixBins);
-            B200_STAMP(3);                                    // group A done: positions are final
+            B200_STAMP(3);                                    // group A done
         } else {
             // publish this tile's counts at once ...
             bar_sync(2, 512);
             const uint32_t total = s_total[bd];
             const uint32_t group = tile / kLookGroup, r = tile % kLookGroup;
-            const bool last_of_group = (LEVELS == 2) && ((r == kLookGroup - 1) || ((size_t)tile + 1 == tiles));
+            const bool last_of_group = (r == kLookGroup - 1) || ((size_t)tile + 1 == tiles);
             uint32_t *row = status_cur + (size_t)tile * kRadixBins + bd;
-            st_relaxed_gpu(row, ((LEVELS == 2 && r == 0) ? kFlagIncl : kFlagLocal) | total);
+            st_relaxed_gpu(row, (r == 0 ? kFlagIncl : kFlagLocal) | total);
             if (status_next != nullptr) {
                 status_next[(size_t)tile * kRadixBins + bd] = 0;
-                if (LEVELS == 2) {
-                    if (last_of_group) status_next[(tiles + group) * kRadixBins + bd] = 0;
-                } else {
-                    const bool end = ((size_t)tile + 1 == tiles);
-                    if (tile % kG1 == kG1 - 1 || end) status_next[(tiles + tile / kG1) * kRadixBins + bd] = 0;
-                    if (tile % kG2 == kG2 - 1 || end) status_next[(tiles + n1 + tile / kG2) * kRadixBins + bd] = 0;
-                }
+                if (last_of_group) status_next[(tiles + group) * kRadixBins + bd] = 0;
             }
             B200_STAMP(10);                                   // published
             // ... resolve the PREVIOUS tile's prefix (everything it needs was published long ago) ...
@@ -1341,11 +1242,9 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
                 st_relaxed_gpu(grow, (group == 0 ? kFlagIncl : kFlagLocal) | (p_in + total));
             }
             __syncwarp();
-            bar_sync(3, 512);                                 // positions are final
             B200_STAMP(3);                                    // group B done
         }
-        // Nobody waits for the other group here: each stages its keys as soon as the positions are
-        // final; the previous tile's offsets (group B's look-back) are only needed for the write below.
+        __syncthreads();                                      // SYNC2: positions final, previous tile's offsets ready
         B200_STAMP(4);
         const uint32_t next = s_misc[8 + ((iter + 1) & 1)];
 
@@ -1369,7 +1268,6 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
         // ---- the next tile's loads go out now and land while the previous tile is written --------
         if (next < tiles) load_tile(next);
         B200_STAMP(6);
-        __syncthreads();                                      // SYNC2: previous tile's offsets ready (and this tile staged)
         if (prev_tile != 0xFFFFFFFFu) write_tile(prev_tile, b ^ 1);
         B200_STAMP(7);                                        // previous tile written
         if (TIMING && g_phase_dbg != nullptr && lane == 0 && (warp == 0 || warp == 8))
@@ -1451,8 +1349,7 @@ struct Variant {
     const char *name;
     int mode;
     int cluster;       // CTAs per cluster (1 = none); 0 marks the persistent pipelined kernel
-    int two_level;     // status rows: 0 one per tile; 1 plus one per group of kLookGroup tiles;
-                       // 3 plus one per 8 tiles plus one per 64 tiles
+    int two_level;     // status rows: one per tile plus one per group of kLookGroup tiles
     int threads;
     int tile;
     size_t smem;
@@ -1487,12 +1384,9 @@ struct Variant {
     { "pipelined2_16w_ipt" #I "_kRankAdd_delayed_twolevel", kRankAdd, 0, 1, 512,                    \
       Pipelined2Shape<I>::kTile, Pipelined2Shape<I>::kSmemBytes, radix_onesweep_pipelined2_kernel<I> }
 
-#define B200_PP3_VARIANT(I)                                                                         \
-    { "pipelined3_16w_ipt" #I "_kRankAdd_delayed_threelevel", kRankAdd, 0, 3, 512,                  \
-      Pipelined2Shape<I>::kTile, Pipelined2Shape<I>::kSmemBytes, radix_onesweep_pipelined2_kernel<I, 0, 3> }
-
 const Variant kVariants[] = {
-    B200_VARIANT(16, 20, 2, kRankAdd, 1),      //  0: 10240-key tiles, 2 CTAs/SM  (default; fastest measured)
+    B200_PP2_VARIANT(18),                      //  0: DEFAULT (fastest measured): persistent CTAs, 9216-key tiles,
+                                               //     delayed two-level look-back
     B200_VARIANT(16, 18, 2, kRankAdd, 1),      //  1: 9216
     B200_VARIANT(16, 16, 2, kRankAdd, 1),      //  2: 8192
     B200_VARIANT(8, 24, 3, kRankAdd, 1),       //  3: 6144, 256 threads
@@ -1534,15 +1428,10 @@ const Variant kVariants[] = {
     B200_VARIANT_T(16, 20, 2, kRankAdd, 1, 296, 1, 1),   // 39: variant 33 with the phase-timing probe
     B200_PP2_VARIANT(20),                             // 40: persistent, delayed two-level look-back, 10240
     B200_PP2_VARIANT(16),                             // 41: 8192
-    B200_PP2_VARIANT(18),                             // 42: 9216
+    B200_VARIANT(16, 20, 2, kRankAdd, 1),             // 42: one tile per CTA, 10240-key tiles (round-1 default until PP2)
     B200_PP2_VARIANT(22),                             // 43: 11264
     { "TIMING_pipelined2_ipt18", kRankAdd, 0, 1, 512, Pipelined2Shape<18>::kTile,
       Pipelined2Shape<18>::kSmemBytes, radix_onesweep_pipelined2_kernel<18, 1> },   // 44
-    B200_PP3_VARIANT(18),                             // 45: three-level, windows loaded together
-    B200_PP3_VARIANT(16),                             // 46
-    B200_PP3_VARIANT(20),                             // 47
-    { "TIMING_pipelined2_threelevel_ipt18", kRankAdd, 0, 3, 512, Pipelined2Shape<18>::kTile,
-      Pipelined2Shape<18>::kSmemBytes, radix_onesweep_pipelined2_kernel<18, 1, 3> },   // 48
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
@@ -1595,7 +1484,6 @@ int ensure_hist_attr() {
 
 // status rows a pass needs: one per tile, plus (pipelined kernel) one per group of tiles
 size_t status_rows(const Variant &var, size_t tiles) {
-    if (var.two_level == 3) return tiles + div_up(tiles, (size_t)kG1) + div_up(tiles, (size_t)kG2);
     return var.two_level ? tiles + div_up(tiles, (size_t)kLookGroup) : tiles;
 }
 
@@ -1665,7 +1553,7 @@ const char *radix_effective_variant_name() { return kVariants[effective_variant(
 
 size_t radix_workspace_bytes(size_t n) {
     const size_t tiles = div_up(n > 0 ? n : 1, kRadixMinTile);
-    const size_t rows = tiles + div_up(tiles, (size_t)kG1) + div_up(tiles, (size_t)kG2) + 2;
+    const size_t rows = tiles + div_up(tiles, (size_t)kPPGroup) + 1;
     return kRadixControlBytes + 2 * rows * kRadixBins * sizeof(uint32_t);
 }
 
