@@ -199,6 +199,8 @@ def bench_main(args, metric: str, unit: str, ClockSampler, peaks_fn) -> None:
             print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})"}))
         return
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep rank 0's stdout to the one JSON line
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     n_local = 1 << args.log2n
