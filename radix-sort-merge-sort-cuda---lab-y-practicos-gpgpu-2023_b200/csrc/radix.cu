@@ -259,43 +259,6 @@ __device__ __forceinline__ uint32_t walk_back(const uint32_t *first, uint32_t ma
     }
 }
 
-// The same walk with its first window (distances 1..W) loaded earlier by window_load, so that two
-// independent walks can have their round trips in flight together.
-template <int W>
-__device__ __forceinline__ void window_load(const uint32_t *first, uint32_t max_dist, uint32_t (&win)[W]) {
-#pragma unroll
-    for (int j = 0; j < W; ++j)
-        win[j] = ((uint32_t)(j + 1) <= max_dist) ? ld_relaxed_gpu(first - (size_t)j * kRadixBins) : kFlagIncl;
-}
-template <int W>
-__device__ __forceinline__ uint32_t walk_back_preloaded(const uint32_t *first, uint32_t max_dist, uint32_t (&win)[W]) {
-    uint32_t acc = 0, back = 1;
-    bool have = true;
-    for (;;) {
-        if (!have) {
-#pragma unroll
-            for (int j = 0; j < W; ++j)
-                win[j] = (back + j <= max_dist) ? ld_relaxed_gpu(first - (size_t)(back + j - 1) * kRadixBins) : kFlagIncl;
-        }
-        have = false;
-        bool done = false;
-        uint32_t used = 0;
-#pragma unroll
-        for (int j = 0; j < W; ++j) {
-            if (!done && used == (uint32_t)j) {
-                const uint32_t f = win[j] & ~kValueMask;
-                if (f != 0) {
-                    acc += win[j] & kValueMask;
-                    used = j + 1;
-                    done = (f == kFlagIncl);
-                }
-            }
-        }
-        if (done) return acc;
-        back += used;
-    }
-}
-
 // CL > 1: the CTAs of a thread-block cluster take CL consecutive tiles and act as ONE link of the
 // look-back chain: tile totals are exchanged through distributed shared memory, the last CTA of
 // the cluster publishes / looks back for all of them and hands the result to its peers.  The
@@ -1160,10 +1123,6 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
         const bool last_of_group = (r == kLookGroup - 1) || ((size_t)pt + 1 == tiles);
         uint32_t *row = status_cur + (size_t)pt * kRadixBins + bd;
         uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
-        // The two walks are independent: the group rows' window goes out first so that both round
-        // trips are in flight together (a dependent round trip costs ~2500 cycles in this kernel).
-        uint32_t w2[W];
-        if (group > 0) window_load<W>(grow - kRadixBins, group, w2);
         uint32_t inprev = p_in;
         if (!p_in_known) {
             inprev = (r > 0) ? walk_back<W>(row - kRadixBins, r) : 0u;
@@ -1171,7 +1130,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
         }
         uint32_t gprev = 0;
         if (group > 0) {
-            gprev = walk_back_preloaded<W>(grow - kRadixBins, group, w2);
+            gprev = walk_back<W>(grow - kRadixBins, group);
             if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + inprev + p_total) & kValueMask));
         }
         s_gofs[buf * kRadixBins + bd] = digit_base + inprev + gprev - s_tstart[buf * kRadixBins + bd];
