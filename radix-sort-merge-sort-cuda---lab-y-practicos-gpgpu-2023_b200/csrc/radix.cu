@@ -32,41 +32,38 @@ namespace b200sort {
 constexpr int kHistThreads = 512;
 constexpr int kHistUnroll  = 4;                  // 128-bit loads in flight per thread
 constexpr int kHistBlocksPerSM = 3;
-// Shared-memory counters are 16-bit and LANE-PRIVATE, one BANK per lane: counter (place p, digit d,
-// lane l) is half (d >> 7) of word (p*128 + (d & 127))*32 + l, so lane l only ever touches bank l.
-// One atomic instruction is one conflict-free wavefront whatever the key distribution (32 random
-// words on 32 banks cost ~3.5, an all-equal input would serialise 32 ways; the first lane-private
-// layout, two lanes per word, still cost 2.2).  16-bit counters overflow after 65535 hits, so the
+// Shared-memory counters are 16-bit and LANE-PRIVATE: counter (place p, digit d, lane l) lives in
+// half (l & 1) of word (p*256 + d)*16 + (l >> 1).  The bank is 16*(d & 1) + (l >> 1), so the only
+// lanes that can ever collide in one atomic instruction are the two lanes of a pair -- at most
+// 2 wavefronts whatever the key distribution (32 random words on 32 banks cost ~3.5, and an
+// all-equal input would serialise 32 ways).  16-bit counters overflow after 65535 hits, so the
 // block flushes to the global histogram every kHistFlushIters iterations (<= 32768 hits each).
-constexpr int kHistSmemWords  = kRadixPasses * (kRadixBins / 2) * 32;            // 64 KiB
+constexpr int kHistSmemWords  = kRadixPasses * kRadixBins * 16;                  // 64 KiB
 constexpr size_t kHistSmemBytes = (size_t)kHistSmemWords * 4;
 constexpr int kHistFlushIters = 128;   // 128 iters * (4 keys * 4 loads) * 16 warps = 32768 per lane column
 
-__device__ __forceinline__ void hist_add(uint32_t *col, int32_t key) {
+__device__ __forceinline__ void hist_add(uint32_t *col, uint32_t one, int32_t key) {
     const uint32_t k = key_bits(key);
-    atomicAdd(col + ((0 * 128 + (k & 127u)) << 5), 1u << ((k >> 3) & 16u));
-    atomicAdd(col + ((1 * 128 + ((k >> 8) & 127u)) << 5), 1u << ((k >> 11) & 16u));
-    atomicAdd(col + ((2 * 128 + ((k >> 16) & 127u)) << 5), 1u << ((k >> 19) & 16u));
-    atomicAdd(col + ((3 * 128 + ((k >> 24) & 127u)) << 5), 1u << ((k >> 27) & 16u));
+    atomicAdd(col + (0 * kRadixBins + (k & 255u)) * 16, one);
+    atomicAdd(col + (1 * kRadixBins + ((k >> 8) & 255u)) * 16, one);
+    atomicAdd(col + (2 * kRadixBins + ((k >> 16) & 255u)) * 16, one);
+    atomicAdd(col + (3 * kRadixBins + (k >> 24)) * 16, one);
 }
 
 // Sum the 32 lane columns of every (place, digit), add into the global histogram, clear.
-// Thread i owns words [i*32, i*32+32) = digits (i & 127) and (i & 127) + 128 of place i >> 7.
 __device__ __forceinline__ void hist_flush(uint32_t *sh, RadixControl *ctl, uint32_t tid) {
-    static_assert(kHistThreads == kRadixPasses * (kRadixBins / 2), "one thread per counter row");
     __syncthreads();
-    uint32_t lo = 0, hi = 0;
+    for (uint32_t i = tid; i < kRadixPasses * kRadixBins; i += kHistThreads) {
+        uint32_t sum = 0;
 #pragma unroll
-    for (uint32_t l = 0; l < 32; ++l) {
-        const uint32_t idx = tid * 32 + ((l + tid) & 31);      // rotate: conflict-free across the warp
-        const uint32_t v = sh[idx];
-        sh[idx] = 0;
-        lo += v & 0xffffu;
-        hi += v >> 16;
+        for (uint32_t w = 0; w < 16; ++w) {
+            const uint32_t idx = i * 16 + ((w + (i >> 1)) & 15);   // rotate: conflict-free across threads
+            const uint32_t v = sh[idx];
+            sh[idx] = 0;
+            sum += (v & 0xffffu) + (v >> 16);
+        }
+        if (sum) atomicAdd(&ctl->hist[i >> kRadixBits][i & (kRadixBins - 1)], sum);
     }
-    const uint32_t p = tid >> 7, d = tid & 127;
-    if (lo) atomicAdd(&ctl->hist[p][d], lo);
-    if (hi) atomicAdd(&ctl->hist[p][d + 128], hi);
     __syncthreads();
 }
 
@@ -97,7 +94,8 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
     }
     __syncthreads();
 
-    uint32_t *col = sh + (tid & 31);
+    uint32_t *col = sh + ((tid & 31) >> 1);
+    const uint32_t one = 1u << (16 * (tid & 1));
 
     // Scalar head up to 16-byte alignment, 128-bit body, scalar tail.
     size_t head = ((16 - (reinterpret_cast<uintptr_t>(keys) & 15)) & 15) / 4;
@@ -120,15 +118,15 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
 #pragma unroll
         for (int u = 0; u < kHistUnroll; ++u) {
             if (ok[u]) {
-                hist_add(col, r[u].x); hist_add(col, r[u].y);
-                hist_add(col, r[u].z); hist_add(col, r[u].w);
+                hist_add(col, one, r[u].x); hist_add(col, one, r[u].y);
+                hist_add(col, one, r[u].z); hist_add(col, one, r[u].w);
             }
         }
         if (++iters == kHistFlushIters) { hist_flush(sh, ctl, tid); iters = 0; }
     }
     if (blockIdx.x == 0) {   // < 8 keys in total: cannot overflow anything
-        for (size_t i = tid; i < head; i += kHistThreads) hist_add(col, keys[i]);
-        for (size_t i = tail_start + tid; i < n; i += kHistThreads) hist_add(col, keys[i]);
+        for (size_t i = tid; i < head; i += kHistThreads) hist_add(col, one, keys[i]);
+        for (size_t i = tail_start + tid; i < n; i += kHistThreads) hist_add(col, one, keys[i]);
     }
     hist_flush(sh, ctl, tid);
 
