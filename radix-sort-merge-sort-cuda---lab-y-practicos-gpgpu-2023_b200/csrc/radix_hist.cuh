@@ -1,0 +1,174 @@
+// radix_hist.cuh -- k1: the digit-histogram kernel of the onesweep radix sort (included by radix.cu).
+#pragma once
+#include "radix.cuh"
+
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace b200sort {
+
+// ================================================================================================
+// k1: digit histograms
+// ================================================================================================
+constexpr int kHistThreads = 512;
+constexpr int kHistUnroll  = 4;                  // 128-bit loads in flight per thread
+constexpr int kHistBlocksPerSM = 3;
+// Shared-memory counters are 16-bit and LANE-PRIVATE: counter (place p, digit d, lane l) lives in
+// half (l & 1) of word (p*256 + d)*16 + (l >> 1).  The bank is 16*(d & 1) + (l >> 1), so the only
+// lanes that can ever collide in one atomic instruction are the two lanes of a pair -- at most
+// 2 wavefronts whatever the key distribution (32 random words on 32 banks cost ~3.5, and an
+// all-equal input would serialise 32 ways).  16-bit counters overflow after 65535 hits, so the
+// block flushes to the global histogram every kHistFlushIters iterations (<= 32768 hits each).
+constexpr int kHistSmemWords  = kRadixPasses * kRadixBins * 16;                  // 64 KiB
+constexpr size_t kHistSmemBytes = (size_t)kHistSmemWords * 4;
+constexpr int kHistFlushIters = 128;   // 128 iters * (4 keys * 4 loads) * 16 warps = 32768 per lane column
+
+__device__ __forceinline__ void hist_add(uint32_t *col, uint32_t one, int32_t key) {
+    const uint32_t k = key_bits(key);
+    atomicAdd(col + (0 * kRadixBins + (k & 255u)) * 16, one);
+    atomicAdd(col + (1 * kRadixBins + ((k >> 8) & 255u)) * 16, one);
+    atomicAdd(col + (2 * kRadixBins + ((k >> 16) & 255u)) * 16, one);
+    atomicAdd(col + (3 * kRadixBins + (k >> 24)) * 16, one);
+}
+
+// Sum the 32 lane columns of every (place, digit), add into the global histogram, clear.
+__device__ __forceinline__ void hist_flush(uint32_t *sh, RadixControl *ctl, uint32_t tid) {
+    __syncthreads();
+    for (uint32_t i = tid; i < kRadixPasses * kRadixBins; i += kHistThreads) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < 16; ++w) {
+            const uint32_t idx = i * 16 + ((w + (i >> 1)) & 15);   // rotate: conflict-free across threads
+            const uint32_t v = sh[idx];
+            sh[idx] = 0;
+            sum += (v & 0xffffu) + (v >> 16);
+        }
+        if (sum) atomicAdd(&ctl->hist[i >> kRadixBits][i & (kRadixBins - 1)], sum);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kHistThreads)
+radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl *ctl,
+                       uint32_t *status_to_zero, size_t status_words, uint32_t skip_enabled,
+                       uint32_t in_place)
+{
+    extern __shared__ __align__(16) uint32_t sh[];
+    __shared__ uint32_t s_warp_sums[kRadixBins / 32];
+    __shared__ uint32_t s_skip[kRadixPasses];
+    __shared__ uint32_t s_hot[kRadixPasses];
+    __shared__ uint32_t s_is_last;
+
+    const uint32_t tid = threadIdx.x;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(sh);
+        for (uint32_t i = tid; i < kHistSmemWords / 4; i += kHistThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
+
+    // Zero the tile-status buffer the first pass will use.
+    if (status_to_zero != nullptr) {
+        uint4 *z = reinterpret_cast<uint4 *>(status_to_zero);
+        const size_t nz = status_words / 4;
+        for (size_t i = (size_t)blockIdx.x * kHistThreads + tid; i < nz;
+             i += (size_t)gridDim.x * kHistThreads)
+            z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    uint32_t *col = sh + ((tid & 31) >> 1);
+    const uint32_t one = 1u << (16 * (tid & 1));
+
+    // Scalar head up to 16-byte alignment, 128-bit body, scalar tail.
+    size_t head = ((16 - (reinterpret_cast<uintptr_t>(keys) & 15)) & 15) / 4;
+    if (head > n) head = n;
+    const size_t nvec = (n - head) / 4;
+    const size_t tail_start = head + nvec * 4;
+    const int4 *v = reinterpret_cast<const int4 *>(keys + head);
+
+    constexpr size_t kChunk = (size_t)kHistThreads * kHistUnroll;
+    int iters = 0;
+    for (size_t base = (size_t)blockIdx.x * kChunk; base < nvec; base += (size_t)gridDim.x * kChunk) {
+        int4 r[kHistUnroll];
+        bool ok[kHistUnroll];
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) {
+            const size_t idx = base + (size_t)u * kHistThreads + tid;
+            ok[u] = idx < nvec;
+            if (ok[u]) r[u] = ld_stream_v4(v + idx);
+        }
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) {
+            if (ok[u]) {
+                hist_add(col, one, r[u].x); hist_add(col, one, r[u].y);
+                hist_add(col, one, r[u].z); hist_add(col, one, r[u].w);
+            }
+        }
+        if (++iters == kHistFlushIters) { hist_flush(sh, ctl, tid); iters = 0; }
+    }
+    if (blockIdx.x == 0) {   // < 8 keys in total: cannot overflow anything
+        for (size_t i = tid; i < head; i += kHistThreads) hist_add(col, one, keys[i]);
+        for (size_t i = tail_start + tid; i < n; i += kHistThreads) hist_add(col, one, keys[i]);
+    }
+    hist_flush(sh, ctl, tid);
+
+    // The last block to finish turns counts into exclusive bases.
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_is_last = (atomicAdd(&ctl->hist_blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;
+    if (tid < kRadixPasses) { s_skip[tid] = 0; s_hot[tid] = 0; }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    for (int p = 0; p < kRadixPasses; ++p) {
+        const uint32_t c = (tid < kRadixBins) ? __ldcg(&ctl->hist[p][tid]) : 0u;
+        uint32_t x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (uint32_t)o) x += y;
+        }
+        if (tid < kRadixBins && lane == 31) s_warp_sums[warp] = x;
+        __syncthreads();
+        if (tid < kRadixBins) {
+            uint32_t add = 0;
+            for (uint32_t w = 0; w < warp; ++w) add += s_warp_sums[w];
+            ctl->base[p][tid] = x - c + add;
+            if (skip_enabled && n > 0 && c == (uint32_t)n) s_skip[p] = 1;
+            if ((size_t)c * 8 > n) s_hot[p] = 1;
+        }
+        __syncthreads();
+    }
+    // The buffer plan: executed pass j reads what pass j-1 wrote (the input for j = 0).
+    //   in place     : writes alternate tmp, out, tmp, ...; an odd count leaves the result in tmp
+    //                  and the final-copy kernel brings it home;
+    //   out of place : writes alternate so that the LAST executed pass lands in out; the input
+    //                  is never written.  No executed pass at all (all keys equal): copy in -> out.
+    if (tid == 0) {
+        uint32_t executed = 0;
+        for (int p = 0; p < kRadixPasses; ++p) executed += s_skip[p] ? 0u : 1u;
+        uint32_t j = 0, cur = kSelIn;
+        for (int p = 0; p < kRadixPasses; ++p) {
+            ctl->skip[p] = s_skip[p];
+            ctl->hot[p] = s_hot[p];
+            ctl->src_sel[p] = cur;
+            uint32_t dst = cur;
+            if (!s_skip[p]) {
+                if (in_place) dst = (j % 2 == 0) ? kSelTmp : kSelOut;
+                else          dst = ((executed - 1 - j) % 2 == 0) ? kSelOut : kSelTmp;
+                ++j;
+                cur = dst;
+            }
+            ctl->dst_sel[p] = dst;
+        }
+        uint32_t final_copy = 0;
+        if (in_place) { if (cur == kSelTmp) final_copy = kSelTmp; }
+        else          { if (executed == 0) final_copy = kSelIn; }
+        ctl->final_copy = final_copy;
+    }
+}
+
+
+}  // namespace b200sort

@@ -1,0 +1,616 @@
+// radix_pipelined.cuh -- k2', k2'': the pass as a persistent, software-pipelined CTA (included by radix.cu).
+#pragma once
+#include "radix_tile.cuh"
+
+namespace b200sort {
+
+// ================================================================================================
+// k2': the same pass as a PERSISTENT, software-pipelined CTA
+// ================================================================================================
+// One CTA per SM slot loops over tiles (tickets).  14 worker warps load / rank / stage / write the
+// keys; 2 chain warps own everything that talks to other tiles (publish the tile's digit counts,
+// decoupled look-back with 128-bit status loads, publish the inclusive counts, global offsets).
+// The workers never wait for the chain on the tile they are ranking: tile i is written out only
+// after tile i+1 has been ranked and staged (double-buffered staging area), and the global loads
+// of tile i+1 are in flight while tile i-1 is being written.  So neither the look-back latency
+// nor the load latency sits on the workers' critical path.
+constexpr int kPPWorkerWarps = 14;
+constexpr int kPPWorkers = kPPWorkerWarps * 32;      // 448
+constexpr int kPPThreads = 512;
+constexpr int kPPChain = kPPThreads - kPPWorkers;    // 64 threads, 4 digits each
+constexpr uint32_t kPPPoison = 0xFFFFFFFFu;
+constexpr int kPPWindow = 8;                         // status rows in flight per chain thread
+enum { kBarW = 1, kBarA = 2, kBarTotals = 3, kBarTstart = 5, kBarGofs = 7 };   // +buffer for the last three
+
+__device__ __forceinline__ void bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const uint32_t *p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_v4(uint32_t *p, uint4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Two-level look-back.  Tiles are grouped kPPGroup at a time.  A tile's prefix is
+//   (sum of the totals of the earlier GROUPS) + (sum of the totals of the earlier tiles of ITS group).
+// Both sums are walks over status rows whose partial values do not depend on any other walk (a
+// tile's own total, a group's own total), so no tile waits for a long serial chain: the inclusive
+// front only has to advance one GROUP per round trip.  (With one level the front must advance one
+// tile per round trip times the window, which is what bounded the pass: ~35 tiles start per
+// microsecond and a status round trip through L2 takes ~0.4 us.)
+constexpr int kPPGroup = kLookGroup;
+
+// Walk back over status rows: row at distance d (1 <= d <= max_dist) is `first - (d-1)*256`; each
+// thread handles four digits with 128-bit loads, W rows in flight.  Flags: 0 not published yet
+// (poll again), kFlagLocal partial (keep walking), kFlagIncl inclusive (stop).  Rows beyond
+// max_dist count as inclusive zero.  acc[k] += everything taken.
+template <int W>
+__device__ __forceinline__ void chain_walk(const uint32_t *first, uint32_t max_dist, uint32_t (&acc)[4]) {
+    uint32_t need[4] = {1, 1, 1, 1};
+    bool done[4] = {false, false, false, false};
+    uint32_t back = 1;
+    for (;;) {
+        uint4 win[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            win[j] = (back + j <= max_dist) ? ld_relaxed_gpu_v4(first - (size_t)(back + j - 1) * kRadixBins)
+                                            : make_uint4(kFlagIncl, kFlagIncl, kFlagIncl, kFlagIncl);
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const uint32_t w4[4] = {win[j].x, win[j].y, win[j].z, win[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!done[k] && need[k] == back + j) {
+                    const uint32_t f = w4[k] & ~kValueMask;
+                    if (f != 0) {
+                        acc[k] += w4[k] & kValueMask;
+                        need[k] += 1;
+                        done[k] = (f == kFlagIncl);
+                    }
+                }
+            }
+        }
+        if (done[0] && done[1] && done[2] && done[3]) break;
+        uint32_t nb = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (!done[k] && need[k] < nb) nb = need[k];
+        back = nb;
+    }
+}
+
+template <int IPT>
+struct PipelinedShape {
+    static constexpr int kTile = kPPWorkers * IPT;
+    static constexpr size_t kSmemBytes =
+        (size_t)kPPWorkerWarps * kRadixBins * 4     // per-warp digit counters -> positions
+        + (size_t)2 * kTile * 4                     // two staging buffers
+        + (size_t)3 * 2 * kRadixBins * 4            // gofs, total, tstart, double-buffered
+        + 128;                                      // warp sums, tickets, tile ids
+};
+
+template <int IPT>
+__global__ void __launch_bounds__(kPPThreads, 2)
+radix_onesweep_pipelined_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
+                                int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
+                                int follow_plan)
+{
+    constexpr int kTile = PipelinedShape<IPT>::kTile;
+    static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in pairs");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *s_table  = reinterpret_cast<uint32_t *>(smem_raw);                     // [14][256]
+    int32_t  *s_keys   = reinterpret_cast<int32_t *>(s_table + kPPWorkerWarps * kRadixBins);   // [2][kTile]
+    uint32_t *s_gofs   = reinterpret_cast<uint32_t *>(s_keys + 2 * kTile);           // [2][256]
+    uint32_t *s_total  = s_gofs + 2 * kRadixBins;                                    // [2][256]
+    uint32_t *s_tstart = s_total + 2 * kRadixBins;                                   // [2][256]
+    uint32_t *s_misc   = s_tstart + 2 * kRadixBins;     // [0..7] warp sums, [8..9] next ticket, [10..11] tile id
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t tiles = (n + kTile - 1) / kTile;
+
+    const int32_t *in = in_buf;
+    int32_t *out = out_buf;
+    if (follow_plan) {
+        if (ctl->skip[pass]) {
+            const size_t rows = tiles + (tiles + kPPGroup - 1) / kPPGroup;       // tile rows + group rows
+            if (status_next != nullptr)
+                for (size_t row = blockIdx.x; row < rows; row += gridDim.x)
+                    if (tid < kRadixBins) status_next[row * kRadixBins + tid] = 0;
+            return;
+        }
+        const uint32_t ss = ctl->src_sel[pass], ds = ctl->dst_sel[pass];
+        in = (ss == kSelIn) ? in_buf : (ss == kSelTmp) ? tmp_buf : out_buf;
+        out = (ds == kSelTmp) ? tmp_buf : out_buf;
+    }
+    const int shift = pass * kRadixBits;
+    const uint32_t flip = (pass == kRadixPasses - 1) ? 0x80u : 0u;
+
+    if (warp >= kPPWorkerWarps) {
+        // ======================== chain warps ========================
+        const uint32_t c4 = (tid - kPPWorkers) * 4;                 // my four digits
+        const uint4 base4 = *reinterpret_cast<const uint4 *>(&ctl->base[pass][c4]);
+        int b = 0;
+        for (;;) {
+            bar_sync(kBarTotals + b, kRadixBins + kPPChain);
+            const uint32_t tile = s_misc[10 + b];
+            if (tile == kPPPoison) break;
+            const uint4 tot = *reinterpret_cast<const uint4 *>(s_total + b * kRadixBins + c4);
+            const uint32_t group = tile / kPPGroup, r = tile % kPPGroup;
+            const bool last_of_group = (r == kPPGroup - 1) || ((size_t)tile + 1 == tiles);
+            uint32_t *row = status_cur + (size_t)tile * kRadixBins + c4;                 // tile rows
+            uint32_t *grow = status_cur + (tiles + group) * kRadixBins + c4;             // group rows follow
+            const uint32_t flag0 = (r == 0) ? kFlagIncl : kFlagLocal;                    // inclusive WITHIN the group
+            st_relaxed_gpu_v4(row, make_uint4(flag0 | tot.x, flag0 | tot.y, flag0 | tot.z, flag0 | tot.w));
+            if (status_next != nullptr) {
+                *reinterpret_cast<uint4 *>(status_next + (size_t)tile * kRadixBins + c4) = make_uint4(0, 0, 0, 0);
+                if (last_of_group)
+                    *reinterpret_cast<uint4 *>(status_next + (tiles + group) * kRadixBins + c4) = make_uint4(0, 0, 0, 0);
+            }
+            // level 1: earlier tiles of my group
+            uint32_t prev[4] = {0, 0, 0, 0};
+            if (r > 0) {
+                chain_walk<kPPWindow>(row - kRadixBins, r, prev);
+                st_relaxed_gpu_v4(row, make_uint4(kFlagIncl | (prev[0] + tot.x), kFlagIncl | (prev[1] + tot.y),
+                                                  kFlagIncl | (prev[2] + tot.z), kFlagIncl | (prev[3] + tot.w)));
+            }
+            // level 2: earlier groups (the last tile of a group owns the group's row)
+            const uint32_t gflag = (group == 0) ? kFlagIncl : kFlagLocal;
+            const uint4 gtot = make_uint4(prev[0] + tot.x, prev[1] + tot.y, prev[2] + tot.z, prev[3] + tot.w);
+            if (last_of_group)
+                st_relaxed_gpu_v4(grow, make_uint4(gflag | gtot.x, gflag | gtot.y, gflag | gtot.z, gflag | gtot.w));
+            if (group > 0) {
+                uint32_t gprev[4] = {0, 0, 0, 0};
+                chain_walk<kPPWindow>(grow - kRadixBins, group, gprev);
+                if (last_of_group)
+                    st_relaxed_gpu_v4(grow, make_uint4(kFlagIncl | ((gprev[0] + gtot.x) & kValueMask),
+                                                       kFlagIncl | ((gprev[1] + gtot.y) & kValueMask),
+                                                       kFlagIncl | ((gprev[2] + gtot.z) & kValueMask),
+                                                       kFlagIncl | ((gprev[3] + gtot.w) & kValueMask)));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) prev[k] += gprev[k];
+            }
+            __syncwarp();
+            bar_sync(kBarTstart + b, kRadixBins + kPPChain);
+            const uint4 ts = *reinterpret_cast<const uint4 *>(s_tstart + b * kRadixBins + c4);
+            *reinterpret_cast<uint4 *>(s_gofs + b * kRadixBins + c4) =
+                make_uint4(base4.x + prev[0] - ts.x, base4.y + prev[1] - ts.y,
+                           base4.z + prev[2] - ts.z, base4.w + prev[3] - ts.w);
+            __threadfence_block();
+            bar_arrive(kBarGofs + b, kPPThreads);
+            b ^= 1;
+        }
+        return;
+    }
+
+    // ============================ worker warps ============================
+    uint32_t *wt = s_table + warp * kRadixBins;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(wt);
+#pragma unroll
+        for (int j = lane; j < kRadixBins / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
+    bar_sync(kBarW, kPPWorkers);
+    uint32_t tile = s_misc[8];
+    uint32_t prev_tile = kPPPoison;
+    const uint32_t wofs = warp * (32 * IPT) + lane;
+
+    int32_t key[IPT];
+    auto load_tile = [&](uint32_t t) {
+        const size_t tile_base = (size_t)t * kTile;
+        const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
+        const int32_t *src = in + tile_base + wofs;
+        if (valid == (uint32_t)kTile) {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) key[i] = ld_stream(src + i * 32);
+        } else {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i)
+                key[i] = (wofs + i * 32 < valid) ? ld_stream(src + i * 32) : 0x7FFFFFFF;
+        }
+    };
+    auto write_tile = [&](uint32_t t, int buf) {
+        const size_t tile_base = (size_t)t * kTile;
+        const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
+        const int32_t *sk = s_keys + buf * kTile;
+        const uint32_t *go = s_gofs + buf * kRadixBins;
+        if (valid == (uint32_t)kTile) {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const uint32_t p = tid + j * kPPWorkers;
+                const int32_t k = sk[p];
+                st_stream(out + (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p), k);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const uint32_t p = tid + j * kPPWorkers;
+                if (p < valid) {
+                    const int32_t k = sk[p];
+                    st_stream(out + (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p), k);
+                }
+            }
+        }
+    };
+
+    if (tile < tiles) load_tile(tile);
+    int b = 0;
+    uint32_t iter = 0;
+    while (tile < tiles) {
+        // ---- rank: one shared-memory atomicAdd per key (lane-ordered; see the self-test) ----------
+        uint32_t rank2[IPT / 2];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint32_t r = atomicAdd(wt + digit_of(key[i], shift, flip), 1u);
+            rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
+        }
+        bar_sync(kBarW, kPPWorkers);
+        // next ticket (everybody has read the slot being overwritten: that read precedes this barrier)
+        if (tid == 0) s_misc[8 + ((iter + 1) & 1)] = atomicAdd(&ctl->ticket[pass], 1u);
+
+        // ---- threads 0..255, thread = digit: totals -> chain; scan; counts -> positions ----------
+        if (tid < kRadixBins) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < kPPWorkerWarps; ++w) total += s_table[w * kRadixBins + tid];
+            s_total[b * kRadixBins + tid] = total;
+            if (tid == 0) s_misc[10 + b] = tile;
+            __threadfence_block();
+            bar_arrive(kBarTotals + b, kRadixBins + kPPChain);
+            uint32_t x = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= (uint32_t)o) x += y;
+            }
+            if (lane == 31) s_misc[warp] = x;
+            bar_sync(kBarA, kRadixBins);
+            uint32_t add = 0;
+#pragma unroll
+            for (int w = 0; w < kRadixBins / 32; ++w) add += (w < (int)warp) ? s_misc[w] : 0u;
+            const uint32_t tile_start = x - total + add;
+            uint32_t run = tile_start;
+#pragma unroll
+            for (int w = 0; w < kPPWorkerWarps; ++w) {
+                const uint32_t c = s_table[w * kRadixBins + tid];
+                s_table[w * kRadixBins + tid] = run;
+                run += c;
+            }
+            s_tstart[b * kRadixBins + tid] = tile_start;
+            __threadfence_block();
+            bar_arrive(kBarTstart + b, kRadixBins + kPPChain);
+        }
+        bar_sync(kBarW, kPPWorkers);                       // positions are final
+        const uint32_t next = s_misc[8 + ((iter + 1) & 1)];
+
+        // ---- stage this tile's keys in digit order ----------------------------------------------------
+        {
+            int32_t *sk = s_keys + b * kTile;
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
+                sk[wt[digit_of(key[i], shift, flip)] + r] = key[i];
+            }
+        }
+        __syncwarp();
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(wt);      // my warp's counters, for the next tile
+#pragma unroll
+            for (int j = lane; j < kRadixBins / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+
+        // ---- loads of the next tile go out now and land while the previous tile is written ----
+        if (next < tiles) load_tile(next);
+        if (prev_tile != kPPPoison) {
+            bar_sync(kBarGofs + (b ^ 1), kPPThreads);      // the chain finished tile i-1 long ago
+            write_tile(prev_tile, b ^ 1);
+        }
+        prev_tile = tile;
+        tile = next;
+        b ^= 1;
+        ++iter;
+    }
+    if (prev_tile != kPPPoison) {
+        bar_sync(kBarW, kPPWorkers);                       // the last tile is fully staged
+        bar_sync(kBarGofs + (b ^ 1), kPPThreads);
+        write_tile(prev_tile, b ^ 1);
+    }
+    if (tid < kRadixBins) {                                // release the chain warps
+        if (tid == 0) s_misc[10 + b] = kPPPoison;
+        __threadfence_block();
+        bar_arrive(kBarTotals + b, kRadixBins + kPPChain);
+    }
+}
+
+// ================================================================================================
+// k2'': persistent CTA, every warp a worker, DELAYED two-level look-back
+// ================================================================================================
+// What the phase probe showed (profiles/r01_phase_timing.txt): a tile needs the counts of the tiles
+// that started a few hundred nanoseconds before it, and those are often not published yet --
+// the look-back does not wait for a long chain but for STRAGGLERS among its ~32 nearest
+// predecessors, 4-5 us of a 9 us tile lifetime, with the SM's registers and shared memory held idle.
+// Here the CTA does not wait: it publishes tile i's counts, then ranks and stages tile i+1, and only
+// then resolves tile i's prefix -- by which time every straggler has long published -- and writes
+// tile i out.  The two-level rows make that possible: a tile's own total and a group's own total do
+// not depend on anybody's look-back, so delaying one's OWN prefix delays nobody else.  Only the last
+// tile of each group sums its group right away (1 tile in 32 waits for stragglers).
+//   tile row  : kFlagLocal = the tile's digit counts, kFlagIncl = inclusive within its group
+//   group row : kFlagLocal = the group's digit counts, kFlagIncl = inclusive over all groups
+template <int IPT>
+struct Pipelined2Shape {
+    static constexpr int kThreads = 512;
+    static constexpr int kTile = kThreads * IPT;
+    static constexpr size_t kSmemBytes =
+        (size_t)16 * kRadixBins * 4                 // per-warp digit counters -> positions
+        + (size_t)2 * kTile * 4                     // two staging buffers
+        + (size_t)(2 + 1 + 2) * kRadixBins * 4      // gofs[2], total, tstart[2]
+        + 128;
+};
+
+template <int IPT, int TIMING = 0>
+__global__ void __launch_bounds__(512, 2)
+radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
+                                 int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
+                                 int follow_plan)
+{
+    constexpr int kThreads = 512, kWarps = 16;
+    constexpr int kTile = Pipelined2Shape<IPT>::kTile;
+    constexpr int W = 8;                                      // status rows in flight per thread
+    static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in pairs");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *s_table  = reinterpret_cast<uint32_t *>(smem_raw);                      // [16][256]
+    int32_t  *s_keys   = reinterpret_cast<int32_t *>(s_table + kWarps * kRadixBins);  // [2][kTile]
+    uint32_t *s_gofs   = reinterpret_cast<uint32_t *>(s_keys + 2 * kTile);            // [2][256]
+    uint32_t *s_total  = s_gofs + 2 * kRadixBins;                                     // [256]
+    uint32_t *s_tstart = s_total + kRadixBins;                                        // [2][256]
+    uint32_t *s_misc   = s_tstart + 2 * kRadixBins;        // [0..7] warp sums, [8..9] tickets
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t tiles = (n + kTile - 1) / kTile;
+
+    const int32_t *in = in_buf;
+    int32_t *out = out_buf;
+    if (follow_plan) {
+        if (ctl->skip[pass]) {
+            const size_t rows = tiles + (tiles + kLookGroup - 1) / kLookGroup;
+            if (status_next != nullptr)
+                for (size_t row = blockIdx.x; row < rows; row += gridDim.x)
+                    if (tid < kRadixBins) status_next[row * kRadixBins + tid] = 0;
+            return;
+        }
+        const uint32_t ss = ctl->src_sel[pass], ds = ctl->dst_sel[pass];
+        in = (ss == kSelIn) ? in_buf : (ss == kSelTmp) ? tmp_buf : out_buf;
+        out = (ds == kSelTmp) ? tmp_buf : out_buf;
+    }
+    const int shift = pass * kRadixBits;
+    const uint32_t flip = (pass == kRadixPasses - 1) ? 0x80u : 0u;
+    const uint32_t lt = lanemask_lt();
+    const bool in_a = tid < kRadixBins;                       // warps 0..7 : thread = digit
+    const bool in_b = !in_a;                                  // warps 8..15: thread - 256 = digit
+    const uint32_t bd = tid - kRadixBins;
+    uint32_t *wt = s_table + warp * kRadixBins;
+    const uint32_t wofs = warp * (32 * IPT) + lane;
+
+    int32_t key[IPT];
+    auto load_tile = [&](uint32_t t) {
+        const size_t tile_base = (size_t)t * kTile;
+        const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
+        const int32_t *src = in + tile_base + wofs;
+        if (valid == (uint32_t)kTile) {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) key[i] = ld_stream(src + i * 32);
+        } else {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i)
+                key[i] = (wofs + i * 32 < valid) ? ld_stream(src + i * 32) : 0x7FFFFFFF;
+        }
+    };
+    auto write_tile = [&](uint32_t t, int buf) {
+        const size_t tile_base = (size_t)t * kTile;
+        const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
+        const int32_t *sk = s_keys + buf * kTile;
+        const uint32_t *go = s_gofs + buf * kRadixBins;
+        if (valid == (uint32_t)kTile) {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const uint32_t p = tid + j * kThreads;
+                const int32_t k = sk[p];
+                st_stream(out + (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p), k);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const uint32_t p = tid + j * kThreads;
+                if (p < valid) {
+                    const int32_t k = sk[p];
+                    st_stream(out + (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p), k);
+                }
+            }
+        }
+    };
+
+    // group B's memory of the previous tile (the one whose prefix is resolved one iteration late)
+    uint32_t digit_base = in_b ? ctl->base[pass][bd] : 0u;
+    uint32_t p_total = 0, p_in = 0;                           // its count of my digit; in-group prefix if known
+    bool p_in_known = false;
+    // The previous tile's look-back, run by group B: fills s_gofs[buf].
+    auto resolve_prev = [&](uint32_t pt, int buf) {
+        const uint32_t group = pt / kLookGroup, r = pt % kLookGroup;
+        const bool last_of_group = (r == kLookGroup - 1) || ((size_t)pt + 1 == tiles);
+        uint32_t *row = status_cur + (size_t)pt * kRadixBins + bd;
+        uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
+        uint32_t inprev = p_in;
+        if (!p_in_known) {
+            inprev = (r > 0) ? walk_back<W>(row - kRadixBins, r) : 0u;
+            if (r > 0) st_relaxed_gpu(row, kFlagIncl | (inprev + p_total));   // shortens later walks
+        }
+        uint32_t gprev = 0;
+        if (group > 0) {
+            gprev = walk_back<W>(grow - kRadixBins, group);
+            if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + inprev + p_total) & kValueMask));
+        }
+        s_gofs[buf * kRadixBins + bd] = digit_base + inprev + gprev - s_tstart[buf * kRadixBins + bd];
+    };
+
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(wt);
+#pragma unroll
+        for (int j = lane; j < kRadixBins / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
+    __syncthreads();
+    uint32_t tile = s_misc[8];
+    uint32_t prev_tile = 0xFFFFFFFFu;
+    if (tile < tiles) load_tile(tile);
+    int b = 0;
+    uint32_t iter = 0;
+
+    while (tile < tiles) {
+        const uint32_t dbg_tile = tile;
+        if (TIMING) { asm volatile("" :: "r"(key[0]), "r"(key[IPT - 1])); }
+        B200_STAMP(0);                                        // this tile's keys are in registers
+        // ---- rank: one shared-memory atomicAdd per key (lane-ordered; see the self-test) ----------
+        uint32_t rank2[IPT / 2];
+        {
+            const uint32_t d0 = digit_of(key[0], shift, flip);
+            const uint32_t agree = __ballot_sync(0xffffffffu, d0 == __shfl_sync(0xffffffffu, d0, 0));
+            const bool hot = (follow_plan && ctl->hot[pass] != 0) || __popc(agree) >= 8;
+            if (!hot) {
+#pragma unroll
+                for (int i = 0; i < IPT; ++i) {
+                    const uint32_t r = atomicAdd(wt + digit_of(key[i], shift, flip), 1u);
+                    rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < IPT; ++i) {
+                    const uint32_t d = digit_of(key[i], shift, flip);
+                    const bool same = (d == __shfl_sync(0xffffffffu, d, 0));
+                    const uint32_t sm = __ballot_sync(0xffffffffu, same);
+                    uint32_t r = 0;
+                    if (!same || lane == 0) r = atomicAdd(wt + d, lane == 0 ? (uint32_t)__popc(sm) : 1u);
+                    const uint32_t r0 = __shfl_sync(0xffffffffu, r, 0);
+                    if (same) r = r0 + __popc(sm & lt);
+                    rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
+                }
+            }
+        }
+        if (TIMING) { asm volatile("" :: "r"(rank2[0]), "r"(rank2[IPT / 2 - 1])); }
+        B200_STAMP(1);                                        // ranked
+        __syncthreads();                                      // SYNC1: counts are final
+        B200_STAMP(2);
+        if (tid == 0) s_misc[8 + ((iter + 1) & 1)] = atomicAdd(&ctl->ticket[pass], 1u);
+
+        if (in_a) {
+            // thread = digit: tile totals -> group B; exclusive scan; warp counts -> positions
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) total += s_table[w * kRadixBins + tid];
+            s_total[tid] = total;
+            __threadfence_block();
+            bar_arrive(2, 512);
+            uint32_t x = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= (uint32_t)o) x += y;
+            }
+            if (lane == 31) s_misc[warp] = x;
+            bar_sync(1, kRadixBins);
+            uint32_t add = 0;
+#pragma unroll
+            for (int w = 0; w < kRadixBins / 32; ++w) add += (w < (int)warp) ? s_misc[w] : 0u;
+            const uint32_t tile_start = x - total + add;
+            uint32_t run = tile_start;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const uint32_t c = s_table[w * kRadixBins + tid];
+                s_table[w * kRadixBins + tid] = run;
+                run += c;
+            }
+            s_tstart[b * kRadixBins + tid] = tile_start;
+            B200_STAMP(3);                                    // group A done
+        } else {
+            // publish this tile's counts at once ...
+            bar_sync(2, 512);
+            const uint32_t total = s_total[bd];
+            const uint32_t group = tile / kLookGroup, r = tile % kLookGroup;
+            const bool last_of_group = (r == kLookGroup - 1) || ((size_t)tile + 1 == tiles);
+            uint32_t *row = status_cur + (size_t)tile * kRadixBins + bd;
+            st_relaxed_gpu(row, (r == 0 ? kFlagIncl : kFlagLocal) | total);
+            if (status_next != nullptr) {
+                status_next[(size_t)tile * kRadixBins + bd] = 0;
+                if (last_of_group) status_next[(tiles + group) * kRadixBins + bd] = 0;
+            }
+            B200_STAMP(10);                                   // published
+            // ... resolve the PREVIOUS tile's prefix (everything it needs was published long ago) ...
+            if (prev_tile != 0xFFFFFFFFu) resolve_prev(prev_tile, b ^ 1);
+            B200_STAMP(11);                                   // previous tile resolved
+            // ... and, for the last tile of a group only, sum the group now so that nobody after
+            // it has to wait an iteration for the group's total
+            p_total = total;
+            p_in_known = false;
+            if (last_of_group) {
+                p_in = (r > 0) ? walk_back<W>(row - kRadixBins, r) : 0u;
+                p_in_known = true;
+                if (r > 0) st_relaxed_gpu(row, kFlagIncl | (p_in + total));
+                uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
+                st_relaxed_gpu(grow, (group == 0 ? kFlagIncl : kFlagLocal) | (p_in + total));
+            }
+            __syncwarp();
+            B200_STAMP(3);                                    // group B done
+        }
+        __syncthreads();                                      // SYNC2: positions final, previous tile's offsets ready
+        B200_STAMP(4);
+        const uint32_t next = s_misc[8 + ((iter + 1) & 1)];
+
+        // ---- stage this tile's keys in digit order ----------------------------------------------------
+        {
+            int32_t *sk = s_keys + b * kTile;
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
+                sk[wt[digit_of(key[i], shift, flip)] + r] = key[i];
+            }
+        }
+        __syncwarp();
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(wt);          // my warp's counters, for the next tile
+#pragma unroll
+            for (int j = lane; j < kRadixBins / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+        B200_STAMP(5);                                        // staged
+        // ---- the next tile's loads go out now and land while the previous tile is written --------
+        if (next < tiles) load_tile(next);
+        B200_STAMP(6);
+        if (prev_tile != 0xFFFFFFFFu) write_tile(prev_tile, b ^ 1);
+        B200_STAMP(7);                                        // previous tile written
+        if (TIMING && g_phase_dbg != nullptr && lane == 0 && (warp == 0 || warp == 8))
+            g_phase_dbg[((size_t)dbg_tile * 2 + (warp >> 3)) * 16 + 9] = tile;
+        prev_tile = tile;
+        tile = next;
+        b ^= 1;
+        ++iter;
+    }
+    // ---- drain: the last tile is staged, its prefix is still to be resolved ----------------------------
+    if (prev_tile != 0xFFFFFFFFu) {
+        __syncthreads();
+        if (in_b) resolve_prev(prev_tile, b ^ 1);
+        __syncthreads();
+        write_tile(prev_tile, b ^ 1);
+    }
+}
+
+
+}  // namespace b200sort
