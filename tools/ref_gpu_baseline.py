@@ -39,6 +39,9 @@ for log2n in range(8, 18):
     run("lab_rand100", log2n)
 for log2n in (8, 9, 10, 11, 12, 14, 16, 17):
     run("uniform_nonneg", log2n)
-run("lab_rand100", 18)
-run("uniform_nonneg", 20)
-run("uniform", 10, timeout=20)          # mixed signs
+run("lab_rand100", 18)                  # launch failure: separators_kernel needs 1026 threads per block
+if "--dangerous" in sys.argv:
+    # recorded once in profiles/r01_reference_gpu_baseline.txt; not repeated by default: the first
+    # faults inside a reference kernel, the second leaves a kernel spinning until the timeout kills it
+    run("uniform_nonneg", 20)
+    run("uniform", 10, timeout=20)      # mixed signs
