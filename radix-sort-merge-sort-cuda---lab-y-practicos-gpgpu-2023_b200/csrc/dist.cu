@@ -21,6 +21,7 @@
 // multisplit is unstable and ranks keys with plain shared-memory atomicAdd.
 #include "dist.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -28,7 +29,7 @@ namespace b200sort {
 
 constexpr int kDistThreads = 512;
 constexpr int kDistIpt = 16;
-constexpr int kDistTile = kDistThreads * kDistIpt;     // 8192 keys per tile
+
 constexpr int kDistMaxWorld = 16;
 
 // ------------------------------------------------------------------------------------------------
@@ -75,22 +76,25 @@ struct DistPartitionArgs {
 // aligned vector of the staging area then maps to a 16-byte aligned vector of the destination, and
 // the interior of every group leaves with 128-bit stores (4x fewer store instructions and 512-byte
 // instead of 128-byte NVLink writes per warp); only group heads and tails use 32-bit stores.
-constexpr int kDistSlots = kDistTile + 4 * kDistMaxWorld;
+
 
 __device__ __forceinline__ void st_stream_v4(int32_t *p, int4 v) {
     asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__global__ void __launch_bounds__(kDistThreads, 2)
+template <int THREADS, int OCC>
+__global__ void __launch_bounds__(THREADS, OCC)
 dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int world,
                       const int *__restrict__ bin_owner, DistPartitionArgs args,
                       unsigned long long *cursor /* [world], zeroed */)
 {
+    constexpr int kTile = THREADS * kDistIpt;
+    constexpr int kSlots = kTile + 4 * kDistMaxWorld;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int32_t *s_keys = reinterpret_cast<int32_t *>(smem_raw);                  // [kDistSlots]
-    uint8_t *s_dest = reinterpret_cast<uint8_t *>(s_keys + kDistSlots);       // [kDistSlots], 0xFF = pad
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_dest + kDistSlots);      // [kDistMaxWorld]
+    int32_t *s_keys = reinterpret_cast<int32_t *>(smem_raw);                  // [kSlots]
+    uint8_t *s_dest = reinterpret_cast<uint8_t *>(s_keys + kSlots);       // [kSlots], 0xFF = pad
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_dest + kSlots);      // [kDistMaxWorld]
     uint32_t *s_start = s_cnt + kDistMaxWorld;                                // [kDistMaxWorld + 2]
     unsigned long long *s_gbase = reinterpret_cast<unsigned long long *>(s_start + kDistMaxWorld + 2);
     uint8_t *s_owner = reinterpret_cast<uint8_t *>(s_gbase + kDistMaxWorld);  // [2^bits]
@@ -98,14 +102,14 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
     const uint32_t tid = threadIdx.x;
     const uint32_t nbins = 1u << bits;
     const int shift = 32 - bits;
-    for (uint32_t i = tid; i < nbins; i += kDistThreads) s_owner[i] = (uint8_t)bin_owner[i];
+    for (uint32_t i = tid; i < nbins; i += THREADS) s_owner[i] = (uint8_t)bin_owner[i];
 
-    const size_t tiles = (n + kDistTile - 1) / kDistTile;
+    const size_t tiles = (n + kTile - 1) / kTile;
     for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const size_t base = tile * kDistTile;
-        const uint32_t valid = (n - base < (size_t)kDistTile) ? (uint32_t)(n - base) : (uint32_t)kDistTile;
+        const size_t base = tile * kTile;
+        const uint32_t valid = (n - base < (size_t)kTile) ? (uint32_t)(n - base) : (uint32_t)kTile;
         if (tid < kDistMaxWorld) s_cnt[tid] = 0;
-        for (uint32_t i = tid; i < kDistSlots / 16; i += kDistThreads)         // every slot starts as a pad
+        for (uint32_t i = tid; i < kSlots / 16; i += THREADS)         // every slot starts as a pad
             reinterpret_cast<uint4 *>(s_dest)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
         __syncthreads();                               // also: s_owner ready, previous tile drained
 
@@ -113,12 +117,12 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
         uint32_t slot[kDistIpt];                       // (dest << 16) | rank inside the tile's dest group
 #pragma unroll
         for (int i = 0; i < kDistIpt; ++i) {
-            const uint32_t p = i * kDistThreads + tid;
+            const uint32_t p = i * THREADS + tid;
             if (p < valid) key[i] = ld_stream(keys + base + p);
         }
 #pragma unroll
         for (int i = 0; i < kDistIpt; ++i) {
-            const uint32_t p = i * kDistThreads + tid;
+            const uint32_t p = i * THREADS + tid;
             if (p < valid) {
                 const uint32_t d = s_owner[key_bits(key[i]) >> shift];
                 slot[i] = (d << 16) | atomicAdd(&s_cnt[d], 1u);
@@ -141,7 +145,7 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < kDistIpt; ++i) {
-            const uint32_t p = i * kDistThreads + tid;
+            const uint32_t p = i * THREADS + tid;
             if (p < valid) {
                 const uint32_t d = slot[i] >> 16;
                 const uint32_t q = s_start[d] + (slot[i] & 0xffffu);
@@ -151,7 +155,7 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
         }
         __syncthreads();
         const uint32_t vectors = (s_start[world] + 3) / 4;
-        for (uint32_t v = tid; v < vectors; v += kDistThreads) {
+        for (uint32_t v = tid; v < vectors; v += THREADS) {
             const uint32_t d4 = reinterpret_cast<const uint32_t *>(s_dest)[v];
             if (d4 == 0xFFFFFFFFu) continue;
             const uint32_t d0 = d4 & 0xFFu;
@@ -174,9 +178,9 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
 // ================================================================================================
 size_t dist_workspace_bytes(size_t, int) { return 256; }    // the destination cursors
 
-static size_t partition_smem(int bits) {
-    return (size_t)kDistSlots * 4 + kDistSlots + (kDistMaxWorld * 2 + 2) * 4 + kDistMaxWorld * 8
-           + ((size_t)1 << bits) + 16;
+static size_t partition_smem(int bits, int threads) {
+    const size_t slots = (size_t)threads * kDistIpt + 4 * kDistMaxWorld;
+    return slots * 4 + slots + (kDistMaxWorld * 2 + 2) * 4 + kDistMaxWorld * 8 + ((size_t)1 << bits) + 16;
 }
 
 int dist_histogram(const int32_t *d_keys, size_t n, int bits, unsigned long long *d_hist, cudaStream_t s) {
@@ -250,19 +254,32 @@ int dist_partition(const int32_t *d_keys, size_t n, int bits, int world, int32_t
     DistPartitionArgs args;
     std::memset(&args, 0, sizeof args);
     for (int r = 0; r < world; ++r) { args.dst_base[r] = h_dst_base[r]; args.dst_offset[r] = h_dst_offset[r]; }
+    // Two compiled shapes: 512 threads x 2 CTAs/SM (8192-key tiles) and 256 threads x 4 CTAs/SM
+    // (4096-key tiles, more tiles in flight per SM).  B200SORT_DIST_SHAPE=1 selects the second.
+    static const int shape = [] { const char *e = getenv("B200SORT_DIST_SHAPE"); return (e && e[0] == '1') ? 1 : 0; }();
     static thread_local bool attr_set = false;
-    const size_t smem = partition_smem(bits);
     if (!attr_set) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel),
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel<512, 2>),
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)partition_smem(B200SORT_DIST_BITS_MAX)));
+                                           (int)partition_smem(B200SORT_DIST_BITS_MAX, 512)));
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel<256, 4>),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)partition_smem(B200SORT_DIST_BITS_MAX, 256)));
         attr_set = true;
     }
     auto *cursor = static_cast<unsigned long long *>(d_ws);
     B200_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long) * kDistMaxWorld, s));
-    const size_t tiles = div_up(n, kDistTile);
-    const unsigned grid = (unsigned)(tiles < (size_t)kNumSMs * 2 ? tiles : (size_t)kNumSMs * 2);
-    dist_partition_kernel<<<grid, kDistThreads, smem, s>>>(d_keys, n, bits, world, d_bin_owner, args, cursor);
+    if (shape == 0) {
+        const size_t tiles = div_up(n, (size_t)512 * kDistIpt);
+        const unsigned grid = (unsigned)(tiles < (size_t)kNumSMs * 2 ? tiles : (size_t)kNumSMs * 2);
+        dist_partition_kernel<512, 2><<<grid, 512, partition_smem(bits, 512), s>>>(d_keys, n, bits, world, d_bin_owner,
+                                                                                  args, cursor);
+    } else {
+        const size_t tiles = div_up(n, (size_t)256 * kDistIpt);
+        const unsigned grid = (unsigned)(tiles < (size_t)kNumSMs * 4 ? tiles : (size_t)kNumSMs * 4);
+        dist_partition_kernel<256, 4><<<grid, 256, partition_smem(bits, 256), s>>>(d_keys, n, bits, world, d_bin_owner,
+                                                                                  args, cursor);
+    }
     B200_LAUNCH_CHECK();
     return B200SORT_OK;
 }
