@@ -230,6 +230,8 @@ def ours_single(args) -> None:
     n = 1 << args.log2n
     if args.variant is not None:
         check(L.b200sort_radix_set_variant(args.variant))
+    if args.merge_variant is not None:
+        check(L.b200sort_merge_set_variant(args.merge_variant))
 
     src = _make_device_keys(torch, n, args.dist, 1, dev)
     out = torch.empty_like(src)
@@ -294,7 +296,8 @@ def ours_single(args) -> None:
         bytes_per_launch = 8.0 * n
         kernels = {"block_sort_ms": acc[0], "merge_passes_ms": acc[1], "merge_passes": passes,
                    "block_sort_gbs": 8.0 * n / (acc[0] / 1e3) / 1e9 if acc[0] > 0 else None,
-                   "tile": int(L.b200sort_block_sort_tile())}
+                   "tile": int(L.b200sort_block_sort_tile()),
+                   "merge_variant": L.b200sort_merge_variant_name(args.merge_variant or 0).decode()}
         dominant = "merge_pass_kernel (+ its partition kernel; one merge pass: 8 B/key)"
         algo_bytes_total = 8.0 * n * (1 + passes)
     achieved = bytes_per_launch / (kernel_ms / 1e3) / 1e9
@@ -373,6 +376,7 @@ def main() -> None:
     ap.add_argument("--dist", default="uniform")
     ap.add_argument("--log2n", type=int, default=28)
     ap.add_argument("--variant", type=int, default=None, help="onesweep tile shape (sweeps only)")
+    ap.add_argument("--merge-variant", type=int, default=None, help="merge-pass kernel (sweeps only)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-log2n", type=int, default=27, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -104,7 +104,8 @@ int b200sort_radix_pass_i32(const int32_t *d_in, int32_t *d_out, size_t n, int p
 /* Keys per tile of the block sort (every aligned run of this many keys comes out sorted). */
 size_t b200sort_block_sort_tile(void);
 int b200sort_block_sort_i32(const int32_t *d_in, int32_t *d_out, size_t n, void *stream);
-/* Same contract, produced by the lab's stages 1-2 (warp split + rank merges; SRM/lab.cu:47-197). */
+/* The same for tiles of b200sort_merge_tile() keys, produced by the lab's stages 1-2 (warp split +
+ * rank merges; SRM/lab.cu:47-197). */
 int b200sort_lab_tile_sort_i32(const int32_t *d_in, int32_t *d_out, size_t n, void *stream);
 /* Keys per output tile of a merge pass. */
 size_t b200sort_merge_tile(void);
@@ -124,6 +125,10 @@ int         b200sort_radix_set_variant(int variant);
 int         b200sort_radix_num_variants(void);
 const char *b200sort_radix_variant_name(int variant);
 size_t      b200sort_radix_tile(void);            /* keys per onesweep tile of the current variant */
+/* The same switch for the compiled merge-pass kernels (0 = default). */
+int         b200sort_merge_set_variant(int variant);
+int         b200sort_merge_num_variants(void);
+const char *b200sort_merge_variant_name(int variant);
 /* The fastest tile shapes rank keys with one shared-memory atomicAdd per key, which is a stable
  * rank only if the GPU resolves same-address lanes of one warp instruction in lane order.  That is
  * observed on B200 but not promised by PTX, so the library runs a self-test once per process

@@ -53,6 +53,9 @@ SIGNATURES = {
     "b200sort_radix_num_variants": (_i, []),
     "b200sort_radix_variant_name": (ctypes.c_char_p, [_i]),
     "b200sort_radix_tile": (_sz, []),
+    "b200sort_merge_set_variant": (_i, [_i]),
+    "b200sort_merge_num_variants": (_i, []),
+    "b200sort_merge_variant_name": (ctypes.c_char_p, [_i]),
     "b200sort_radix_set_skip": (_i, [_i]),
     "b200sort_debug_set_phase_buffer": (_i, [_vp]),
     "b200sort_radix_atomic_order_ok": (_i, []),

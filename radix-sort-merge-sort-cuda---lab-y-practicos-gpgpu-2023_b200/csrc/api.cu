@@ -342,6 +342,9 @@ int b200sort_merge_pass_i32(const int32_t *d_in, int32_t *d_out, size_t n, size_
     return merge_pass(d_in, d_out, n, run, d_splits, static_cast<cudaStream_t>(stream));
 }
 
+int b200sort_merge_set_variant(int variant) { return merge_set_variant(variant); }
+int b200sort_merge_num_variants(void) { return merge_num_variants(); }
+const char *b200sort_merge_variant_name(int variant) { return merge_variant_name(variant); }
 int b200sort_radix_set_variant(int variant) { return radix_set_variant(variant); }
 int b200sort_radix_num_variants(void) { return radix_num_variants(); }
 const char *b200sort_radix_variant_name(int variant) { return radix_variant_name(variant); }

@@ -17,6 +17,8 @@
 // invisible in the output but it keeps the partition consistent between k4 and k5.
 #include "merge.cuh"
 
+#include <atomic>
+
 namespace b200sort {
 
 constexpr int kSortThreads = 256;
@@ -28,6 +30,11 @@ constexpr int kSortTile    = kSortThreads * kSortK;   // 4096
 __device__ __forceinline__ uint32_t pad(uint32_t i) { return i + (i >> 5); }
 // + K + 1: the serial merge reads one element ahead and, past the end of a ragged tile, up to K on.
 constexpr int kSortSmemWords = (kSortTile + kSortK + 1) + ((kSortTile + kSortK + 1) >> 5) + 1;
+
+__device__ __forceinline__ void st_stream_v4(int32_t *p, int32_t a, int32_t b, int32_t c, int32_t d) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 __device__ __forceinline__ void cas(int32_t &a, int32_t &b, bool ascending) {
     const bool sw = ascending ? (a > b) : (a < b);
@@ -82,32 +89,49 @@ __device__ __forceinline__ void serial_merge(const int32_t *s, uint32_t a_ptr, u
 // ------------------------------------------------------------------------------------------------
 // k3
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSortThreads)
+// THREADS = 256: 4096-key tiles; THREADS = 512: 8192-key tiles (one more round in shared memory, one
+// global merge pass less).  Full, 16-byte-aligned tiles are loaded and stored with 128-bit accesses
+// straight from / to the 16 consecutive keys a thread owns.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
 block_sort_kernel(const int32_t *in, int32_t *out, size_t n)
 {
-    __shared__ int32_t s[kSortSmemWords];
+    constexpr int kTile = THREADS * kSortK;
+    constexpr int kWords = (kTile + kSortK + 1) + ((kTile + kSortK + 1) >> 5) + 1;
+    __shared__ int32_t s[kWords];
     const uint32_t tid = threadIdx.x;
-    const size_t tile_base = (size_t)blockIdx.x * kSortTile;
-    const uint32_t valid = (n - tile_base < (size_t)kSortTile) ? (uint32_t)(n - tile_base) : (uint32_t)kSortTile;
-
-    // coalesced load; the tail is padded with INT_MAX, which sorts last
-#pragma unroll
-    for (int j = 0; j < kSortK; ++j) {
-        const uint32_t i = j * kSortThreads + tid;
-        s[pad(i)] = (i < valid) ? ld_stream(in + tile_base + i) : 0x7FFFFFFF;
-    }
-    if (tid == 0) { s[pad(kSortTile)] = 0x7FFFFFFF; }
-    __syncthreads();
+    const size_t tile_base = (size_t)blockIdx.x * kTile;
+    const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
+    const bool direct = valid == (uint32_t)kTile &&
+                        ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
 
     int32_t key[kSortK];
+    if (direct) {
+        const int4 *src = reinterpret_cast<const int4 *>(in + tile_base + (size_t)tid * kSortK);
 #pragma unroll
-    for (int k = 0; k < kSortK; ++k) key[k] = s[pad(tid * kSortK + k)];
+        for (int q = 0; q < kSortK / 4; ++q) {
+            const int4 v = ld_stream_v4(src + q);
+            key[4 * q] = v.x; key[4 * q + 1] = v.y; key[4 * q + 2] = v.z; key[4 * q + 3] = v.w;
+        }
+        if (tid == 0) s[pad(kTile)] = 0x7FFFFFFF;
+    } else {
+        // coalesced load; the tail is padded with INT_MAX, which sorts last
+#pragma unroll
+        for (int j = 0; j < kSortK; ++j) {
+            const uint32_t i = j * THREADS + tid;
+            s[pad(i)] = (i < valid) ? ld_stream(in + tile_base + i) : 0x7FFFFFFF;
+        }
+        if (tid == 0) s[pad(kTile)] = 0x7FFFFFFF;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kSortK; ++k) key[k] = s[pad(tid * kSortK + k)];
+        __syncthreads();
+    }
     thread_bitonic_sort<kSortK>(key);
-    __syncthreads();
 
     // merge rounds: sorted runs of len -> 2*len
 #pragma unroll 1
-    for (uint32_t len = kSortK; len < (uint32_t)kSortTile; len <<= 1) {
+    for (uint32_t len = kSortK; len < (uint32_t)kTile; len <<= 1) {
 #pragma unroll
         for (int k = 0; k < kSortK; ++k) s[pad(tid * kSortK + k)] = key[k];
         __syncthreads();
@@ -119,12 +143,19 @@ block_sort_kernel(const int32_t *in, int32_t *out, size_t n)
         __syncthreads();
     }
 
+    if (direct) {
+        int32_t *dst = out + tile_base + (size_t)tid * kSortK;
+#pragma unroll
+        for (int q = 0; q < kSortK / 4; ++q)
+            st_stream_v4(dst + 4 * q, key[4 * q], key[4 * q + 1], key[4 * q + 2], key[4 * q + 3]);
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < kSortK; ++k) s[pad(tid * kSortK + k)] = key[k];
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kSortK; ++j) {
-        const uint32_t i = j * kSortThreads + tid;
+        const uint32_t i = j * THREADS + tid;
         if (i < valid) st_stream(out + tile_base + i, s[pad(i)]);
     }
 }
@@ -329,10 +360,180 @@ merge_pass_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, siz
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k5' (default): the same pass with far fewer instructions per key
+// ------------------------------------------------------------------------------------------------
+// What ncu showed for k5 (profiles/r01_merge.md): ~50 warp instructions per 32 keys at 1.4 IPC and four
+// barriers per tile; nothing else is near a limit (HBM 32 %, shared-memory pipe 40 %).  Here
+//   * each slice is followed by a gap of kGap slots whose first kSortK + 1 hold sentinels (INT_MAX),
+//     so the serial merge needs no bounds tests: out = min(a, b), one compare, one load.  A sentinel
+//     can only be taken in place of a key that is itself INT_MAX, and then every key still to come
+//     is INT_MAX too, so the values are exact.  kGap = 32 keeps the padded address of "element i of
+//     the tile" a per-thread constant plus a compile-time offset (+33 words if it belongs to B);
+//   * every thread ends with 16 CONSECUTIVE outputs in registers and stores them as four 128-bit
+//     stores straight to global memory -- no second trip through shared memory, no barriers for it;
+//   * the staging area is double-buffered: one barrier per tile;
+//   * run lengths that are powers of two (every pass of merge_sort) take shifts, not 64-bit divisions.
+constexpr int kGap = 32;
+constexpr int kPass2Logical = kSortTile + 2 * kGap;
+constexpr int kPass2Words = kPass2Logical + (kPass2Logical >> 5) + 1;
+static_assert(kGap % 32 == 0 && kGap >= kSortK + 1, "see the staging stores");
+
+// A = s[0 .. na), B = s[b_base .. b_base + nb) (logical indices, padded on access).
+__device__ __forceinline__ uint32_t merge_path_gap(const int32_t *s, uint32_t na, uint32_t b_base,
+                                                   uint32_t nb, uint32_t diag) {
+    uint32_t lo = diag > nb ? diag - nb : 0, hi = diag < na ? diag : na;
+    const uint32_t b_last = b_base + diag - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const int32_t a = s[pad(mid)];
+        const int32_t b = s[pad(b_last - mid)];
+        if (a <= b) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// K outputs from (a_ptr, b_ptr); both runs end in at least K + 1 sentinels.
+template <int K>
+__device__ __forceinline__ void serial_merge_sentinel(const int32_t *s, uint32_t a_ptr, uint32_t b_ptr,
+                                                      int32_t (&out)[K]) {
+    int32_t a_val = s[pad(a_ptr)], b_val = s[pad(b_ptr)];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const bool take_a = a_val <= b_val;                // ties: A first (SRM/lab.cu:163-170)
+        out[k] = take_a ? a_val : b_val;
+        const uint32_t nxt = (take_a ? a_ptr : b_ptr) + 1;
+        const int32_t v = s[pad(nxt)];
+        a_ptr = take_a ? nxt : a_ptr;  a_val = take_a ? v : a_val;
+        b_ptr = take_a ? b_ptr : nxt;  b_val = take_a ? b_val : v;
+    }
+}
+
+// The tile's two slices as 32-bit element offsets into `in` (n <= B200SORT_MAX_N = 2^30).
+// pair_shift >= 0: 2 * run == 1 << pair_shift (shifts instead of 64-bit divisions).
+struct MergeTileGeom32 { uint32_t oa, ob, na, nb; };
+__device__ __forceinline__ MergeTileGeom32 merge_tile_geom32(const int32_t *in, size_t n, size_t run, int pair_shift,
+                                                             uint32_t sp0, uint32_t sp1, size_t t) {
+    MergeTileGeom32 g;
+    if (pair_shift < 0) {
+        const MergeTileGeom w = merge_tile_geom(in, n, run, sp0, sp1, t);
+        g.oa = (uint32_t)(w.a - in); g.ob = (uint32_t)(w.b - in); g.na = w.na; g.nb = w.nb;
+        return g;
+    }
+    const uint32_t n32 = (uint32_t)n, run32 = (uint32_t)run;
+    const uint32_t g0 = (uint32_t)t * kSortTile;
+    const uint32_t base = (g0 >> pair_shift) << pair_shift;
+    const uint32_t rest = n32 - base;
+    const uint32_t la = rest < run32 ? rest : run32;
+    const uint32_t lb = rest - la < run32 ? rest - la : run32;
+    const uint32_t diag0 = g0 - base;
+    const uint32_t pair_len = la + lb;
+    const uint32_t diag1 = diag0 + kSortTile < pair_len ? diag0 + kSortTile : pair_len;
+    const uint32_t a1 = (diag1 == pair_len) ? la : sp1;
+    g.oa = base + sp0;
+    g.ob = base + la + (diag0 - sp0);
+    g.na = a1 - sp0;
+    g.nb = (diag1 - a1) - (diag0 - sp0);
+    return g;
+}
+
+__global__ void __launch_bounds__(kSortThreads, 4)
+merge_pass2_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, size_t n, size_t run,
+                   int pair_shift, const uint32_t *__restrict__ splits, size_t tiles)
+{
+    __shared__ int32_t s2[2][kPass2Words];
+    const uint32_t tid = threadIdx.x;
+    size_t t = blockIdx.x;
+    if (t >= tiles) return;
+    const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const uint32_t padtid = pad(tid);
+
+    int32_t next_keys[kSortK];
+    MergeTileGeom32 geo = merge_tile_geom32(in, n, run, pair_shift, __ldg(splits + t), __ldg(splits + t + 1), t);
+    uint32_t sp0 = 0, sp1 = 0;
+    if (t + gridDim.x < tiles) { sp0 = __ldg(splits + t + gridDim.x); sp1 = __ldg(splits + t + gridDim.x + 1); }
+    auto fetch = [&](const MergeTileGeom32 &g) {
+        const uint32_t total = g.na + g.nb;
+        const uint32_t ia = g.oa + tid;                        // element i of the tile is in[ia + i - tid] ...
+        const uint32_t ib = g.ob + tid - g.na;                 // ... or in[ib + i - tid] once i >= na  (ob >= na)
+#pragma unroll
+        for (int j = 0; j < kSortK; ++j) {
+            const uint32_t i = j * kSortThreads + tid;
+            const int32_t *src = in + ((i < g.na) ? ia : ib);
+            next_keys[j] = (i < total) ? ld_stream(src + j * kSortThreads) : 0x7FFFFFFF;
+        }
+    };
+    fetch(geo);
+    int buf = 0;
+    for (;;) {
+        int32_t *s = s2[buf];
+        const uint32_t na = geo.na, nb = geo.nb, total = na + nb;
+        const size_t g0 = t * kSortTile;
+        // element i = j * 256 + tid sits at pad(i) = pad(tid) + j * 264, B's elements kGap slots further
+        // on: pad(i + 32) = pad(i) + 33
+        {
+            int32_t *sa = s + padtid, *sb = sa + kGap + kGap / 32;
+#pragma unroll
+            for (int j = 0; j < kSortK; ++j) {
+                const uint32_t i = j * kSortThreads + tid;
+                int32_t *dst = (i < na) ? sa : sb;
+                dst[j * (kSortThreads + kSortThreads / 32)] = next_keys[j];
+            }
+        }
+        if (tid <= kSortK) s[pad(na + tid)] = 0x7FFFFFFF;                                        // after A
+        else if (tid >= 32 && tid <= 32 + kSortK) s[pad(total + kGap + (tid - 32))] = 0x7FFFFFFF;   // after B
+        __syncthreads();    // the only barrier of the tile: the other buffer was last read a tile ago
+
+        // the next tile's loads go out now and land while this tile is merged
+        const size_t t_next = t + gridDim.x;
+        const bool more = t_next < tiles;
+        if (more) {
+            geo = merge_tile_geom32(in, n, run, pair_shift, sp0, sp1, t_next);
+            fetch(geo);
+            const size_t t_after = t_next + gridDim.x;
+            if (t_after < tiles) { sp0 = __ldg(splits + t_after); sp1 = __ldg(splits + t_after + 1); }
+        }
+
+        const uint32_t first = tid * kSortK;
+        const uint32_t diag = first < total ? first : total;
+        const uint32_t ai = merge_path_gap(s, na, na + kGap, nb, diag);
+        int32_t key[kSortK];
+        serial_merge_sentinel<kSortK>(s, ai, na + kGap + (diag - ai), key);
+        int32_t *dst = out + g0 + first;
+        if (total == (uint32_t)kSortTile && out_aligned) {
+#pragma unroll
+            for (int q = 0; q < kSortK / 4; ++q)
+                st_stream_v4(dst + 4 * q, key[4 * q], key[4 * q + 1], key[4 * q + 2], key[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kSortK; ++k)
+                if (first + k < total) st_stream(dst + k, key[k]);
+        }
+        if (!more) break;
+        t = t_next;
+        buf ^= 1;
+    }
+}
+
 // ================================================================================================
 // host side
 // ================================================================================================
-size_t merge_block_tile() { return kSortTile; }
+// bit 0: merge pass = k5 (staged output, bounds-tested serial merge) instead of k5'
+// bit 1: block sort tiles of 4096 keys (256 threads) instead of 8192 (512 threads)
+static std::atomic<int> g_merge_variant{0};
+int merge_set_variant(int v) {
+    if (v < 0 || v > 3) return B200SORT_ERR_INVALID;
+    g_merge_variant.store(v);
+    return B200SORT_OK;
+}
+int merge_num_variants() { return 4; }
+const char *merge_variant_name(int v) {
+    static const char *names[4] = {"block8192_pass2_sentinel_direct_store", "block8192_pass1_staged_store",
+                                   "block4096_pass2_sentinel_direct_store", "block4096_pass1_staged_store"};
+    return (v >= 0 && v < 4) ? names[v] : nullptr;
+}
+
+size_t merge_block_tile() { return (g_merge_variant.load() & 2) ? kSortTile : 2 * kSortTile; }
 size_t merge_tile() { return kSortTile; }
 
 size_t merge_workspace_bytes(size_t n) {
@@ -343,8 +544,10 @@ int merge_block_sort(const int32_t *d_in, int32_t *d_out, size_t n, cudaStream_t
     if (n == 0) return B200SORT_OK;
     if (lab_stages)
         lab_tile_sort_kernel<<<(unsigned)div_up(n, kSortTile), kSortThreads, 0, s>>>(d_in, d_out, n);
+    else if (merge_block_tile() == (size_t)kSortTile)
+        block_sort_kernel<kSortThreads><<<(unsigned)div_up(n, kSortTile), kSortThreads, 0, s>>>(d_in, d_out, n);
     else
-        block_sort_kernel<<<(unsigned)div_up(n, kSortTile), kSortThreads, 0, s>>>(d_in, d_out, n);
+        block_sort_kernel<2 * kSortThreads><<<(unsigned)div_up(n, 2 * kSortTile), 2 * kSortThreads, 0, s>>>(d_in, d_out, n);
     B200_LAUNCH_CHECK();
     return B200SORT_OK;
 }
@@ -364,8 +567,15 @@ int merge_pass(const int32_t *d_in, int32_t *d_out, size_t n, size_t run, const 
     if (run == 0 || run % kSortTile != 0) return B200SORT_ERR_INVALID;
     const size_t tiles = div_up(n, kSortTile);
     const size_t slots = (size_t)kNumSMs * 4;              // persistent: 4 CTAs of 256 threads per SM
-    merge_pass_kernel<<<(unsigned)(tiles < slots ? tiles : slots), kSortThreads, 0, s>>>(d_in, d_out, n, run,
-                                                                                        d_splits, tiles);
+    const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
+    if ((g_merge_variant.load() & 1) == 0)
+    {
+        int pair_shift = -1;                                   // 2 * run a power of two: shifts instead of divisions
+        if ((run & (run - 1)) == 0) { pair_shift = 1; while (((size_t)1 << pair_shift) < 2 * run) ++pair_shift; }
+        merge_pass2_kernel<<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tiles);
+    }
+    else
+        merge_pass_kernel<<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, d_splits, tiles);
     B200_LAUNCH_CHECK();
     return B200SORT_OK;
 }
@@ -380,8 +590,9 @@ int merge_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, vo
     }
     if (d_ws == nullptr || ws_bytes < merge_workspace_bytes(n)) return B200SORT_ERR_WORKSPACE;
     auto *splits = static_cast<uint32_t *>(d_ws);
+    const size_t first_run = lab_stages ? (size_t)kSortTile : merge_block_tile();
     int passes = 0;
-    for (size_t run = kSortTile; run < n; run *= 2) ++passes;
+    for (size_t run = first_run; run < n; run *= 2) ++passes;
     // Land the final pass in d_out: the block sort (which may run in place) writes to whichever
     // buffer makes that so.  d_in is only ever read by the block sort.
     int32_t *src = (passes % 2 == 0) ? d_out : d_tmp;
@@ -393,7 +604,7 @@ int merge_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, vo
     }
     B200_TRY(merge_block_sort(d_in, src, n, s, lab_stages));
     if (ms) B200_CUDA_TRY(cudaEventRecord(ev[1], s));
-    for (size_t run = kSortTile; run < n; run *= 2) {
+    for (size_t run = first_run; run < n; run *= 2) {
         B200_TRY(merge_partition(src, n, run, splits, s));
         B200_TRY(merge_pass(src, dst, n, run, splits, s));
         int32_t *t = src; src = dst; dst = t;

@@ -7,6 +7,10 @@ namespace b200sort {
 size_t merge_block_tile();
 size_t merge_tile();
 size_t merge_workspace_bytes(size_t n);
+// A/B switch between the compiled merge-pass kernels (0 = default); process-wide, for sweeps.
+int merge_set_variant(int v);
+int merge_num_variants();
+const char *merge_variant_name(int v);
 
 // lab_stages: produce the sorted tiles with the assignment's staged pipeline (1-bit warp split +
 // in-block rank merges) instead of the register bitonic network + merge-path rounds.

@@ -77,6 +77,10 @@ struct Variant {
     { "pipelined2_16w_ipt" #I "_kRankAdd_delayed_twolevel", kRankAdd, 0, 1, 512,                    \
       Pipelined2Shape<I>::kTile, Pipelined2Shape<I>::kSmemBytes, radix_onesweep_pipelined2_kernel<I> }
 
+#define B200_PP2X_VARIANT(I, S, P)                                                                  \
+    { "pipelined2_16w_ipt" #I "_split" #S "_pack" #P, kRankAdd, 0, 1, 512, Pipelined2Shape<I, P>::kTile, \
+      Pipelined2Shape<I, P>::kSmemBytes, radix_onesweep_pipelined2_kernel<I, 0, S, P> }
+
 const Variant kVariants[] = {
     B200_PP2_VARIANT(18),                      //  0: DEFAULT (fastest measured): persistent CTAs, 9216-key tiles,
                                                //     delayed two-level look-back
@@ -125,6 +129,12 @@ const Variant kVariants[] = {
     B200_PP2_VARIANT(22),                             // 43: 11264
     { "TIMING_pipelined2_ipt18", kRankAdd, 0, 1, 512, Pipelined2Shape<18>::kTile,
       Pipelined2Shape<18>::kSmemBytes, radix_onesweep_pipelined2_kernel<18, 1> },   // 44
+    B200_PP2X_VARIANT(18, 1, 0),                      // 45: the previous tile's two look-back walks split over the groups
+    B200_PP2X_VARIANT(18, 0, 1),                      // 46: 16-bit counters, two warps per row
+    B200_PP2X_VARIANT(18, 1, 1),                      // 47: both
+    B200_PP2X_VARIANT(20, 1, 1),                      // 48: both, 10240-key tiles
+    B200_PP2X_VARIANT(16, 1, 1),                      // 49: both, 8192-key tiles
+    B200_PP2X_VARIANT(20, 0, 1),                      // 50: packed counters, 10240-key tiles
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);

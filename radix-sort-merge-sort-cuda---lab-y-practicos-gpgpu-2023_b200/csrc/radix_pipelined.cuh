@@ -345,35 +345,42 @@ radix_onesweep_pipelined_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t
 // tile of each group sums its group right away (1 tile in 32 waits for stragglers).
 //   tile row  : kFlagLocal = the tile's digit counts, kFlagIncl = inclusive within its group
 //   group row : kFlagLocal = the group's digit counts, kFlagIncl = inclusive over all groups
-template <int IPT>
+// SPLIT: the previous tile's two look-back walks run concurrently, one per thread group (see below).
+// PACK : two warps share one row of digit counters, 16 bits each (8 rows instead of 16): half the
+//        shared-memory traffic of the digit phase and of the zeroing.
+template <int IPT, int PACK = 0>
 struct Pipelined2Shape {
     static constexpr int kThreads = 512;
     static constexpr int kTile = kThreads * IPT;
+    static constexpr int kRows = PACK ? 8 : 16;
     static constexpr size_t kSmemBytes =
-        (size_t)16 * kRadixBins * 4                 // per-warp digit counters -> positions
+        (size_t)kRows * kRadixBins * 4              // per-warp digit counters -> positions
         + (size_t)2 * kTile * 4                     // two staging buffers
-        + (size_t)(2 + 1 + 2) * kRadixBins * 4      // gofs[2], total, tstart[2]
+        + (size_t)(2 + 1 + 2 + 1) * kRadixBins * 4  // gofs[2], total, tstart[2], previous tile's group prefix
         + 128;
 };
 
-template <int IPT, int TIMING = 0>
+template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0>
 __global__ void __launch_bounds__(512, 2)
 radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                  int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
                                  int follow_plan)
 {
-    constexpr int kThreads = 512, kWarps = 16;
-    constexpr int kTile = Pipelined2Shape<IPT>::kTile;
+    constexpr int kThreads = 512;
+    constexpr int kTile = Pipelined2Shape<IPT, PACK>::kTile;
+    constexpr int kRows = Pipelined2Shape<IPT, PACK>::kRows;
     constexpr int W = 8;                                      // status rows in flight per thread
     static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in pairs");
+    static_assert(kTile + 64 < 65536, "PACK keeps 16-bit positions");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *s_table  = reinterpret_cast<uint32_t *>(smem_raw);                      // [16][256]
-    int32_t  *s_keys   = reinterpret_cast<int32_t *>(s_table + kWarps * kRadixBins);  // [2][kTile]
+    uint32_t *s_table  = reinterpret_cast<uint32_t *>(smem_raw);                      // [kRows][256]
+    int32_t  *s_keys   = reinterpret_cast<int32_t *>(s_table + kRows * kRadixBins);   // [2][kTile]
     uint32_t *s_gofs   = reinterpret_cast<uint32_t *>(s_keys + 2 * kTile);            // [2][256]
     uint32_t *s_total  = s_gofs + 2 * kRadixBins;                                     // [256]
     uint32_t *s_tstart = s_total + kRadixBins;                                        // [2][256]
-    uint32_t *s_misc   = s_tstart + 2 * kRadixBins;        // [0..7] warp sums, [8..9] tickets
+    uint32_t *s_g2     = s_tstart + 2 * kRadixBins;           // [256] SPLIT: previous tile's prefix over earlier groups
+    uint32_t *s_misc   = s_g2 + kRadixBins;                   // [0..7] warp sums, [8..9] tickets
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t tiles = (n + kTile - 1) / kTile;
@@ -398,8 +405,21 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
     const bool in_a = tid < kRadixBins;                       // warps 0..7 : thread = digit
     const bool in_b = !in_a;                                  // warps 8..15: thread - 256 = digit
     const uint32_t bd = tid - kRadixBins;
-    uint32_t *wt = s_table + warp * kRadixBins;
+    // my warp's counters: a row of its own, or (PACK) one 16-bit half of the row it shares with warp ^ 1
+    uint32_t *wt = s_table + (PACK ? (warp >> 1) : warp) * kRadixBins;
+    const uint32_t sh = PACK ? (warp & 1) * 16 : 0;
     const uint32_t wofs = warp * (32 * IPT) + lane;
+    auto my_half = [&](uint32_t word) -> uint32_t { return PACK ? ((word >> sh) & 0xffffu) : word; };
+    auto zero_counters = [&]() {
+        uint4 *z = reinterpret_cast<uint4 *>(wt);
+        if (PACK) {
+            z[(warp & 1) * 32 + lane] = make_uint4(0, 0, 0, 0);      // each warp of the pair clears half the row
+        } else {
+#pragma unroll
+            for (int j = lane; j < kRadixBins / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
+        }
+    };
+    auto pair_bar = [&]() { bar_sync(3 + (warp >> 1), 64); };     // the two warps that share a counter row
 
     int32_t key[IPT];
     auto load_tile = [&](uint32_t t) {
@@ -443,7 +463,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
     uint32_t digit_base = in_b ? ctl->base[pass][bd] : 0u;
     uint32_t p_total = 0, p_in = 0;                           // its count of my digit; in-group prefix if known
     bool p_in_known = false;
-    // The previous tile's look-back, run by group B: fills s_gofs[buf].
+    // !SPLIT: the previous tile's look-back, run by group B alone: fills s_gofs[buf].
     auto resolve_prev = [&](uint32_t pt, int buf) {
         const uint32_t group = pt / kLookGroup, r = pt % kLookGroup;
         const bool last_of_group = (r == kLookGroup - 1) || ((size_t)pt + 1 == tiles);
@@ -461,12 +481,66 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
         }
         s_gofs[buf * kRadixBins + bd] = digit_base + inprev + gprev - s_tstart[buf * kRadixBins + bd];
     };
-
-    {
-        uint4 *z = reinterpret_cast<uint4 *>(wt);
+    // SPLIT: the two walks are given to the two groups and started before anything else in the digit
+    // phase, because a dependent global round trip costs ~2500 cycles in this kernel (it queues behind
+    // the shared-memory traffic of both CTAs on the SM):
+    //   group A (thread = digit) loads the first window of GROUP rows, does its digit work while the
+    //           loads are in flight, finishes the walk and leaves the prefix in s_g2;
+    //   group B (thread = digit) walks the TILE rows of the previous tile's group, then publishes this
+    //           tile's counts, and after SYNC2 combines both prefixes into s_gofs[buf].
+    constexpr int W1 = 12, W2 = 8;               // (16, 8) and (8, 8) spill; this pair does not
+    uint32_t win2[W2];
+    auto level2_load = [&](uint32_t pt) {
+        const uint32_t group = pt / kLookGroup;
+        const uint32_t *first = status_cur + (tiles + group) * kRadixBins + tid - kRadixBins;
 #pragma unroll
-        for (int j = lane; j < kRadixBins / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
-    }
+        for (int j = 0; j < W2; ++j)
+            win2[j] = ((uint32_t)(j + 1) <= group) ? ld_relaxed_gpu(first - (size_t)j * kRadixBins) : kFlagIncl;
+    };
+    auto level2_finish = [&](uint32_t pt) {
+        const uint32_t group = pt / kLookGroup;
+        const uint32_t *first = status_cur + (tiles + group) * kRadixBins + tid - kRadixBins;
+        uint32_t acc = 0, back = 1;
+        bool have = true;
+        for (;;) {
+            if (!have) {
+#pragma unroll
+                for (int j = 0; j < W2; ++j)
+                    win2[j] = (back + j <= group) ? ld_relaxed_gpu(first - (size_t)(back + j - 1) * kRadixBins) : kFlagIncl;
+            }
+            have = false;
+            bool done = false;
+            uint32_t used = 0;
+#pragma unroll
+            for (int j = 0; j < W2; ++j) {
+                if (!done && used == (uint32_t)j) {
+                    const uint32_t f = win2[j] & ~kValueMask;
+                    if (f != 0) { acc += win2[j] & kValueMask; used = j + 1; done = (f == kFlagIncl); }
+                }
+            }
+            if (done) break;
+            back += used;
+        }
+        s_g2[tid] = acc;
+    };
+    auto level1 = [&](uint32_t pt) -> uint32_t {       // group B
+        if (p_in_known) return p_in;                 // the last tile of a group summed its group when it published
+        const uint32_t r = pt % kLookGroup;
+        uint32_t *row = status_cur + (size_t)pt * kRadixBins + bd;
+        const uint32_t in = (r > 0) ? walk_back<W1>(row - kRadixBins, r) : 0u;
+        if (r > 0) st_relaxed_gpu(row, kFlagIncl | (in + p_total));        // shortens later walks
+        return in;
+    };
+    auto combine_prev = [&](uint32_t pt, int buf, uint32_t q_total, uint32_t q_in) {   // group B, after A's level2_finish
+        const uint32_t group = pt / kLookGroup;
+        const bool last = (pt % kLookGroup == kLookGroup - 1) || ((size_t)pt + 1 == tiles);
+        const uint32_t gprev = s_g2[bd];
+        if (last && group > 0)
+            st_relaxed_gpu(status_cur + (tiles + group) * kRadixBins + bd, kFlagIncl | ((gprev + q_in + q_total) & kValueMask));
+        s_gofs[buf * kRadixBins + bd] = digit_base + q_in + gprev - s_tstart[buf * kRadixBins + bd];
+    };
+
+    zero_counters();
     if (tid == 0) s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
     __syncthreads();
     uint32_t tile = s_misc[8];
@@ -479,6 +553,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
         const uint32_t dbg_tile = tile;
         if (TIMING) { asm volatile("" :: "r"(key[0]), "r"(key[IPT - 1])); }
         B200_STAMP(0);                                        // this tile's keys are in registers
+        if (PACK) pair_bar();                                 // my partner has cleared its half of our counter row
         // ---- rank: one shared-memory atomicAdd per key (lane-ordered; see the self-test) ----------
         uint32_t rank2[IPT / 2];
         {
@@ -488,7 +563,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
             if (!hot) {
 #pragma unroll
                 for (int i = 0; i < IPT; ++i) {
-                    const uint32_t r = atomicAdd(wt + digit_of(key[i], shift, flip), 1u);
+                    const uint32_t r = my_half(atomicAdd(wt + digit_of(key[i], shift, flip), 1u << sh));
                     rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
                 }
             } else {
@@ -498,7 +573,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
                     const bool same = (d == __shfl_sync(0xffffffffu, d, 0));
                     const uint32_t sm = __ballot_sync(0xffffffffu, same);
                     uint32_t r = 0;
-                    if (!same || lane == 0) r = atomicAdd(wt + d, lane == 0 ? (uint32_t)__popc(sm) : 1u);
+                    if (!same || lane == 0) r = my_half(atomicAdd(wt + d, (lane == 0 ? (uint32_t)__popc(sm) : 1u) << sh));
                     const uint32_t r0 = __shfl_sync(0xffffffffu, r, 0);
                     if (same) r = r0 + __popc(sm & lt);
                     rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
@@ -511,11 +586,17 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
         B200_STAMP(2);
         if (tid == 0) s_misc[8 + ((iter + 1) & 1)] = atomicAdd(&ctl->ticket[pass], 1u);
 
+        const bool have_prev = prev_tile != 0xFFFFFFFFu;
+        uint32_t q_total_keep = 0, q_in_keep = 0;             // SPLIT, group B: the previous tile's count and in-group prefix
         if (in_a) {
+            if (SPLIT && have_prev && prev_tile / kLookGroup > 0) level2_load(prev_tile);
             // thread = digit: tile totals -> group B; exclusive scan; warp counts -> positions
             uint32_t total = 0;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) total += s_table[w * kRadixBins + tid];
+            for (int w = 0; w < kRows; ++w) {
+                const uint32_t c = s_table[w * kRadixBins + tid];
+                total += PACK ? (c & 0xffffu) + (c >> 16) : c;
+            }
             s_total[tid] = total;
             __threadfence_block();
             bar_arrive(2, 512);
@@ -533,15 +614,28 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
             const uint32_t tile_start = x - total + add;
             uint32_t run = tile_start;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
+            for (int w = 0; w < kRows; ++w) {
                 const uint32_t c = s_table[w * kRadixBins + tid];
-                s_table[w * kRadixBins + tid] = run;
-                run += c;
+                if (PACK) {                                   // warp 2w's keys first, then warp 2w+1's
+                    const uint32_t lo = c & 0xffffu;
+                    s_table[w * kRadixBins + tid] = run | ((run + lo) << 16);
+                    run += lo + (c >> 16);
+                } else {
+                    s_table[w * kRadixBins + tid] = run;
+                    run += c;
+                }
             }
             s_tstart[b * kRadixBins + tid] = tile_start;
+            if (SPLIT && have_prev) { if (prev_tile / kLookGroup > 0) level2_finish(prev_tile); else s_g2[tid] = 0; }
             B200_STAMP(3);                                    // group A done
         } else {
-            // publish this tile's counts at once ...
+            if (SPLIT) {
+                // the previous tile's in-group prefix first (it needs nothing from this tile) ...
+                q_total_keep = p_total;
+                if (have_prev) q_in_keep = level1(prev_tile);
+                B200_STAMP(11);                               // previous tile: level-1 prefix known
+            }
+            // ... publish this tile's counts ...
             bar_sync(2, 512);
             const uint32_t total = s_total[bd];
             const uint32_t group = tile / kLookGroup, r = tile % kLookGroup;
@@ -553,9 +647,11 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
                 if (last_of_group) status_next[(tiles + group) * kRadixBins + bd] = 0;
             }
             B200_STAMP(10);                                   // published
-            // ... resolve the PREVIOUS tile's prefix (everything it needs was published long ago) ...
-            if (prev_tile != 0xFFFFFFFFu) resolve_prev(prev_tile, b ^ 1);
-            B200_STAMP(11);                                   // previous tile resolved
+            if (!SPLIT) {
+                // ... resolve the PREVIOUS tile's prefix (everything it needs was published long ago) ...
+                if (have_prev) resolve_prev(prev_tile, b ^ 1);
+                B200_STAMP(11);                               // previous tile resolved
+            }
             // ... and, for the last tile of a group only, sum the group now so that nobody after
             // it has to wait an iteration for the group's total
             p_total = total;
@@ -570,7 +666,8 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
             __syncwarp();
             B200_STAMP(3);                                    // group B done
         }
-        __syncthreads();                                      // SYNC2: positions final, previous tile's offsets ready
+        __syncthreads();                                      // SYNC2: positions final; previous tile: offsets (SPLIT: both prefixes) known
+        if (SPLIT && in_b && have_prev) combine_prev(prev_tile, b ^ 1, q_total_keep, q_in_keep);
         B200_STAMP(4);
         const uint32_t next = s_misc[8 + ((iter + 1) & 1)];
 
@@ -580,21 +677,21 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
 #pragma unroll
             for (int i = 0; i < IPT; ++i) {
                 const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
-                sk[wt[digit_of(key[i], shift, flip)] + r] = key[i];
+                sk[my_half(wt[digit_of(key[i], shift, flip)]) + r] = key[i];
             }
         }
-        __syncwarp();
-        {
-            uint4 *z = reinterpret_cast<uint4 *>(wt);          // my warp's counters, for the next tile
-#pragma unroll
-            for (int j = lane; j < kRadixBins / 4; j += 32) z[j] = make_uint4(0, 0, 0, 0);
-        }
-        __syncwarp();
+        // the counters are cleared for the next tile once nobody reads positions from them any more
+        if (PACK && !SPLIT) pair_bar(); else __syncwarp();
+        if (!(PACK && SPLIT)) { zero_counters(); __syncwarp(); }
         B200_STAMP(5);                                        // staged
         // ---- the next tile's loads go out now and land while the previous tile is written --------
         if (next < tiles) load_tile(next);
         B200_STAMP(6);
-        if (prev_tile != 0xFFFFFFFFu) write_tile(prev_tile, b ^ 1);
+        if (SPLIT) {
+            __syncthreads();                                  // SYNC3: the previous tile's offsets are in s_gofs
+            if (PACK) zero_counters();
+        }
+        if (have_prev) write_tile(prev_tile, b ^ 1);
         B200_STAMP(7);                                        // previous tile written
         if (TIMING && g_phase_dbg != nullptr && lane == 0 && (warp == 0 || warp == 8))
             g_phase_dbg[((size_t)dbg_tile * 2 + (warp >> 3)) * 16 + 9] = tile;
@@ -606,7 +703,15 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
     // ---- drain: the last tile is staged, its prefix is still to be resolved ----------------------------
     if (prev_tile != 0xFFFFFFFFu) {
         __syncthreads();
-        if (in_b) resolve_prev(prev_tile, b ^ 1);
+        if (SPLIT) {
+            uint32_t q_in = 0;
+            if (in_a) { if (prev_tile / kLookGroup > 0) { level2_load(prev_tile); level2_finish(prev_tile); } else s_g2[tid] = 0; }
+            else q_in = level1(prev_tile);
+            __syncthreads();
+            if (in_b) combine_prev(prev_tile, b ^ 1, p_total, q_in);
+        } else {
+            if (in_b) resolve_prev(prev_tile, b ^ 1);
+        }
         __syncthreads();
         write_tile(prev_tile, b ^ 1);
     }

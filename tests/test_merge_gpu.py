@@ -31,7 +31,8 @@ def test_partition_points_match_cpu_merge_path_and_pass_merges():
     import torch
     T = lib().b200sort_merge_tile()
     for n, run, dist in ((8 * T, T, "uniform"), (8 * T, 2 * T, "and3"), (5 * T + 100, T, "uniform"),
-                         (6 * T + 1, 4 * T, "edge_mix"), (4 * T, 2 * T, "ascending"), (4 * T, 2 * T, "descending")):
+                         (6 * T + 1, 4 * T, "edge_mix"), (4 * T, 2 * T, "ascending"), (4 * T, 2 * T, "descending"),
+                         (7 * T + 5, 3 * T, "uniform"), (600 * T + 77, 8 * T, "uniform")):
         keys = datagen.make(dist, n, 9)
         runs = keys.copy()
         for base in range(0, n, run):
@@ -64,6 +65,34 @@ def test_merge_sort_bit_exact(dist, n):
                      f"{dist} n={n}")
 
 
+def test_every_merge_pass_kernel_bit_exact():
+    """All compiled merge-pass kernels (b200sort_merge_set_variant), incl. ragged tails, unaligned
+    output (scalar-store path), INT_MAX keys next to the sentinels and runs of equal keys."""
+    import torch
+    L = lib()
+    cases = [(d, n) for d in ("uniform", "edge_mix", "all_equal", "and3", "descending", "skewed90")
+             for n in (4097, 8192, 40000, 100001, (1 << 20) + 4099)]
+    int_max = np.full(3 * 4096 + 5, np.iinfo(np.int32).max, np.int32); int_max[::7] = 5
+    try:
+        for v in range(L.b200sort_merge_num_variants()):
+            assert L.b200sort_merge_set_variant(v) == 0
+            name = L.b200sort_merge_variant_name(v).decode()
+            for dist, n in cases:
+                keys = datagen.make(dist, n, 31)
+                assert_bit_exact(gpu_sort(keys, ALGO_MERGE), oracle.radix_sort(keys), f"{name} {dist} n={n}")
+            assert_bit_exact(gpu_sort(int_max, ALGO_MERGE), oracle.radix_sort(int_max), f"{name} INT_MAX")
+            # unaligned buffers: keys and scratch start 4 bytes past a 16-byte boundary
+            keys = datagen.uniform(50001, 3)
+            buf = to_device(np.concatenate([np.zeros(1, np.int32), keys])); d = buf[1:]
+            tmp = torch.empty(50002, dtype=torch.int32, device="cuda")[1:]
+            ws, ptr, nbytes = workspace(50001, ALGO_MERGE)
+            check(L.b200sort_merge_i32(d.data_ptr(), tmp.data_ptr(), 50001, ptr, nbytes, stream_ptr()))
+            torch.cuda.synchronize()
+            assert_bit_exact(d.cpu().numpy(), oracle.radix_sort(keys), f"{name} unaligned")
+    finally:
+        L.b200sort_merge_set_variant(0)
+
+
 def test_golden_vectors_from_the_reference(golden_small, golden_mixed):
     for name, (keys, ref_out) in golden_small.items():
         assert_bit_exact(gpu_sort(keys, ALGO_MERGE), ref_out, name)
@@ -93,7 +122,7 @@ def test_full_size_properties_2_28(dist):
 
 def test_lab_tile_sort_sorts_every_tile():
     import torch
-    T = lib().b200sort_block_sort_tile()
+    T = lib().b200sort_merge_tile()
     for dist, n in (("uniform", 6 * T), ("edge_mix", 2 * T + 33), ("descending", T), ("lab_rand100", 3000), ("all_equal", 70)):
         keys = datagen.make(dist, n, 6)
         d_in = to_device(keys); d_out = torch.empty_like(d_in)
