@@ -31,9 +31,18 @@ __device__ __forceinline__ uint32_t pad(uint32_t i) { return i + (i >> 5); }
 // + K + 1: the serial merge reads one element ahead and, past the end of a ragged tile, up to K on.
 constexpr int kSortSmemWords = (kSortTile + kSortK + 1) + ((kSortTile + kSortK + 1) >> 5) + 1;
 
-__device__ __forceinline__ void st_stream_v4(int32_t *p, int32_t a, int32_t b, int32_t c, int32_t d) {
-    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
-                 :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+// 256-bit global accesses (sm_100+): a thread that owns 16 consecutive keys moves them as two full
+// 32-byte sectors.  (128-bit accesses at a 64-byte lane stride write half sectors and cost twice the
+// load/store-pipe wavefronts: measured slower than staging through shared memory.)
+__device__ __forceinline__ void st_stream_v8(int32_t *p, const int32_t *k) {
+    asm volatile("st.global.L1::no_allocate.v8.s32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(k[0]), "r"(k[1]), "r"(k[2]), "r"(k[3]), "r"(k[4]), "r"(k[5]), "r"(k[6]), "r"(k[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_stream_v8(const int32_t *p, int32_t *k) {
+    asm volatile("ld.global.L1::no_allocate.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(k[0]), "=r"(k[1]), "=r"(k[2]), "=r"(k[3]), "=r"(k[4]), "=r"(k[5]), "=r"(k[6]), "=r"(k[7])
+                 : "l"(p) : "memory");
 }
 
 __device__ __forceinline__ void cas(int32_t &a, int32_t &b, bool ascending) {
@@ -90,7 +99,7 @@ __device__ __forceinline__ void serial_merge(const int32_t *s, uint32_t a_ptr, u
 // k3
 // ------------------------------------------------------------------------------------------------
 // THREADS = 256: 4096-key tiles; THREADS = 512: 8192-key tiles (one more round in shared memory, one
-// global merge pass less).  Full, 16-byte-aligned tiles are loaded and stored with 128-bit accesses
+// global merge pass less).  Full, 32-byte-aligned tiles are loaded and stored with 256-bit accesses
 // straight from / to the 16 consecutive keys a thread owns.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
@@ -103,16 +112,13 @@ block_sort_kernel(const int32_t *in, int32_t *out, size_t n)
     const size_t tile_base = (size_t)blockIdx.x * kTile;
     const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
     const bool direct = valid == (uint32_t)kTile &&
-                        ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+                        ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
 
     int32_t key[kSortK];
     if (direct) {
-        const int4 *src = reinterpret_cast<const int4 *>(in + tile_base + (size_t)tid * kSortK);
+        const int32_t *src = in + tile_base + (size_t)tid * kSortK;
 #pragma unroll
-        for (int q = 0; q < kSortK / 4; ++q) {
-            const int4 v = ld_stream_v4(src + q);
-            key[4 * q] = v.x; key[4 * q + 1] = v.y; key[4 * q + 2] = v.z; key[4 * q + 3] = v.w;
-        }
+        for (int q = 0; q < kSortK / 8; ++q) ld_stream_v8(src + 8 * q, key + 8 * q);
         if (tid == 0) s[pad(kTile)] = 0x7FFFFFFF;
     } else {
         // coalesced load; the tail is padded with INT_MAX, which sorts last
@@ -146,8 +152,7 @@ block_sort_kernel(const int32_t *in, int32_t *out, size_t n)
     if (direct) {
         int32_t *dst = out + tile_base + (size_t)tid * kSortK;
 #pragma unroll
-        for (int q = 0; q < kSortK / 4; ++q)
-            st_stream_v4(dst + 4 * q, key[4 * q], key[4 * q + 1], key[4 * q + 2], key[4 * q + 3]);
+        for (int q = 0; q < kSortK / 8; ++q) st_stream_v8(dst + 8 * q, key + 8 * q);
         return;
     }
 #pragma unroll
@@ -370,7 +375,7 @@ merge_pass_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, siz
 //     can only be taken in place of a key that is itself INT_MAX, and then every key still to come
 //     is INT_MAX too, so the values are exact.  kGap = 32 keeps the padded address of "element i of
 //     the tile" a per-thread constant plus a compile-time offset (+33 words if it belongs to B);
-//   * every thread ends with 16 CONSECUTIVE outputs in registers and stores them as four 128-bit
+//   * every thread ends with 16 CONSECUTIVE outputs in registers and stores them as two 256-bit
 //     stores straight to global memory -- no second trip through shared memory, no barriers for it;
 //   * the staging area is double-buffered: one barrier per tile;
 //   * run lengths that are powers of two (every pass of merge_sort) take shifts, not 64-bit divisions.
@@ -445,7 +450,7 @@ merge_pass2_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, si
     const uint32_t tid = threadIdx.x;
     size_t t = blockIdx.x;
     if (t >= tiles) return;
-    const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
     const uint32_t padtid = pad(tid);
 
     int32_t next_keys[kSortK];
@@ -502,8 +507,7 @@ merge_pass2_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, si
         int32_t *dst = out + g0 + first;
         if (total == (uint32_t)kSortTile && out_aligned) {
 #pragma unroll
-            for (int q = 0; q < kSortK / 4; ++q)
-                st_stream_v4(dst + 4 * q, key[4 * q], key[4 * q + 1], key[4 * q + 2], key[4 * q + 3]);
+            for (int q = 0; q < kSortK / 8; ++q) st_stream_v8(dst + 8 * q, key + 8 * q);
         } else {
 #pragma unroll
             for (int k = 0; k < kSortK; ++k)

@@ -135,6 +135,8 @@ const Variant kVariants[] = {
     B200_PP2X_VARIANT(20, 1, 1),                      // 48: both, 10240-key tiles
     B200_PP2X_VARIANT(16, 1, 1),                      // 49: both, 8192-key tiles
     B200_PP2X_VARIANT(20, 0, 1),                      // 50: packed counters, 10240-key tiles
+    B200_PP2X_VARIANT(22, 0, 1),                      // 51: 11264
+    B200_PP2X_VARIANT(24, 0, 1),                      // 52: 12288
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-1 second session: A/B of the split/packed onesweep shapes and of the new merge kernels.
-# usage: gpu_r1b.sh "<radix variants>" "<merge variants>" [ncu]
+# usage: gpu_r1b.sh "<radix variants>" "<merge variants>" [ncu kernel regex] [ncu launches to skip]
 mkdir -p gpurun_out
 echo "== pytest (all onesweep shapes, merge)"
 timeout 900 python -m pytest tests/test_radix_gpu.py -m gpu -q -x --timeout 300 -p no:cacheprovider -k "all_tile_shapes or single_pass" 2>&1 | tail -3
@@ -20,6 +20,6 @@ except Exception as e: print('merge variant failed', $m, e)
 " | tee -a gpurun_out/variants_r1b.txt; done
 if [ -n "$3" ]; then
   CMDM="python bench.py --algo merge --log2n 26 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1"
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'merge_pass2|block_sort' -s 24 -c 2 -o gpurun_out/r01b_merge $CMDM > gpurun_out/r01b_ncu_merge.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$3" -s ${4:-24} -c 2 -o gpurun_out/r01b_merge $CMDM > gpurun_out/r01b_ncu_merge.log 2>&1
   echo "ncu merge exit $?"
 fi
