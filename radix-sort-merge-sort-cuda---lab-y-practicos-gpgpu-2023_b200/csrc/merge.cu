@@ -98,10 +98,56 @@ __device__ __forceinline__ void serial_merge(const int32_t *s, uint32_t a_ptr, u
 // ------------------------------------------------------------------------------------------------
 // k3
 // ------------------------------------------------------------------------------------------------
+// 32 sorted runs of K keys (one per lane, in registers) -> one sorted run of 32 * K keys in blocked
+// order (lane l ends with elements [l*K, l*K + K)), by bitonic merging: no shared memory, no searches.
+// Element index i = lane * K + k.  Merging two sorted halves of a block of m = lanes * K elements:
+// first i meets m - 1 - i  (= lane ^ (lanes - 1), register K - 1 - k), the smaller stays low; then
+// the half-cleaners i ^ j for j = m/4 ... K across lanes (shuffles) and j = K/2 ... 1 in registers.
+// (ncu of the block sort with all rounds in shared memory: load/store pipe 92 % busy, 7 wavefronts
+// per 32 keys and round; a shuffle stage is one.)
+template <int K>
+__device__ __forceinline__ void warp_bitonic_merge_rounds(int32_t (&key)[K], uint32_t lane) {
+    constexpr uint32_t full = 0xffffffffu;
+#pragma unroll
+    for (int lanes = 2; lanes <= 32; lanes <<= 1) {
+        {
+            const bool low = (lane & (lanes >> 1)) == 0;
+#pragma unroll
+            for (int k = 0; k < K / 2; ++k) {
+                const int32_t a = key[k], b = key[K - 1 - k];
+                const int32_t pb = __shfl_xor_sync(full, b, lanes - 1);   // partner's key[K-1-k] meets my key[k]
+                const int32_t pa = __shfl_xor_sync(full, a, lanes - 1);   // partner's key[k] meets my key[K-1-k]
+                key[k] = low ? min(a, pb) : max(a, pb);
+                key[K - 1 - k] = low ? min(b, pa) : max(b, pa);
+            }
+        }
+#pragma unroll
+        for (int j = lanes >> 2; j >= 1; j >>= 1) {
+            const bool low = (lane & j) == 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int32_t v = __shfl_xor_sync(full, key[k], j);
+                key[k] = low ? min(key[k], v) : max(key[k], v);
+            }
+        }
+#pragma unroll
+        for (int j = K >> 1; j >= 1; j >>= 1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if ((k & j) == 0) {
+                    const int32_t a = min(key[k], key[k | j]), b = max(key[k], key[k | j]);
+                    key[k] = a; key[k | j] = b;
+                }
+            }
+        }
+    }
+}
+
 // THREADS = 256: 4096-key tiles; THREADS = 512: 8192-key tiles (one more round in shared memory, one
 // global merge pass less).  Full, 32-byte-aligned tiles are loaded and stored with 256-bit accesses
 // straight from / to the 16 consecutive keys a thread owns.
-template <int THREADS>
+// WARPNET: the rounds 16 -> 512 run as a bitonic network over the warp's registers.
+template <int THREADS, int WARPNET>
 __global__ void __launch_bounds__(THREADS)
 block_sort_kernel(const int32_t *in, int32_t *out, size_t n)
 {
@@ -134,10 +180,11 @@ block_sort_kernel(const int32_t *in, int32_t *out, size_t n)
         __syncthreads();
     }
     thread_bitonic_sort<kSortK>(key);
+    if (WARPNET) warp_bitonic_merge_rounds<kSortK>(key, tid & 31);
 
     // merge rounds: sorted runs of len -> 2*len
 #pragma unroll 1
-    for (uint32_t len = kSortK; len < (uint32_t)kTile; len <<= 1) {
+    for (uint32_t len = WARPNET ? 32 * kSortK : kSortK; len < (uint32_t)kTile; len <<= 1) {
 #pragma unroll
         for (int k = 0; k < kSortK; ++k) s[pad(tid * kSortK + k)] = key[k];
         __syncthreads();
@@ -524,17 +571,21 @@ merge_pass2_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, si
 // ================================================================================================
 // bit 0: merge pass = k5 (staged output, bounds-tested serial merge) instead of k5'
 // bit 1: block sort tiles of 4096 keys (256 threads) instead of 8192 (512 threads)
+// bit 2: block sort with every round in shared memory (no warp-register bitonic rounds)
 static std::atomic<int> g_merge_variant{0};
 int merge_set_variant(int v) {
-    if (v < 0 || v > 3) return B200SORT_ERR_INVALID;
+    if (v < 0 || v > 7) return B200SORT_ERR_INVALID;
     g_merge_variant.store(v);
     return B200SORT_OK;
 }
-int merge_num_variants() { return 4; }
+int merge_num_variants() { return 8; }
 const char *merge_variant_name(int v) {
-    static const char *names[4] = {"block8192_pass2_sentinel_direct_store", "block8192_pass1_staged_store",
-                                   "block4096_pass2_sentinel_direct_store", "block4096_pass1_staged_store"};
-    return (v >= 0 && v < 4) ? names[v] : nullptr;
+    static const char *names[8] = {
+        "block8192_warpnet_pass2_sentinel_direct_store", "block8192_warpnet_pass1_staged_store",
+        "block4096_warpnet_pass2_sentinel_direct_store", "block4096_warpnet_pass1_staged_store",
+        "block8192_smemrounds_pass2_sentinel_direct_store", "block8192_smemrounds_pass1_staged_store",
+        "block4096_smemrounds_pass2_sentinel_direct_store", "block4096_smemrounds_pass1_staged_store"};
+    return (v >= 0 && v < 8) ? names[v] : nullptr;
 }
 
 size_t merge_block_tile() { return (g_merge_variant.load() & 2) ? kSortTile : 2 * kSortTile; }
@@ -548,10 +599,14 @@ int merge_block_sort(const int32_t *d_in, int32_t *d_out, size_t n, cudaStream_t
     if (n == 0) return B200SORT_OK;
     if (lab_stages)
         lab_tile_sort_kernel<<<(unsigned)div_up(n, kSortTile), kSortThreads, 0, s>>>(d_in, d_out, n);
-    else if (merge_block_tile() == (size_t)kSortTile)
-        block_sort_kernel<kSortThreads><<<(unsigned)div_up(n, kSortTile), kSortThreads, 0, s>>>(d_in, d_out, n);
-    else
-        block_sort_kernel<2 * kSortThreads><<<(unsigned)div_up(n, 2 * kSortTile), 2 * kSortThreads, 0, s>>>(d_in, d_out, n);
+    else {
+        const bool small = merge_block_tile() == (size_t)kSortTile, net = (g_merge_variant.load() & 4) == 0;
+        const unsigned g1 = (unsigned)div_up(n, kSortTile), g2 = (unsigned)div_up(n, 2 * kSortTile);
+        if (small && net)       block_sort_kernel<kSortThreads, 1><<<g1, kSortThreads, 0, s>>>(d_in, d_out, n);
+        else if (small)         block_sort_kernel<kSortThreads, 0><<<g1, kSortThreads, 0, s>>>(d_in, d_out, n);
+        else if (net)           block_sort_kernel<2 * kSortThreads, 1><<<g2, 2 * kSortThreads, 0, s>>>(d_in, d_out, n);
+        else                    block_sort_kernel<2 * kSortThreads, 0><<<g2, 2 * kSortThreads, 0, s>>>(d_in, d_out, n);
+    }
     B200_LAUNCH_CHECK();
     return B200SORT_OK;
 }

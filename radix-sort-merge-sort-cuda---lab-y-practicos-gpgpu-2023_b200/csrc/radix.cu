@@ -8,8 +8,9 @@
 //        skippable, flags hot digits, plans the buffers and zeroes the first status buffer.   4 B/key
 //   k2  one pass, 8 B/key, in three compiled families (b200sort_radix_set_variant picks a shape):
 //        radix_onesweep_pipelined2_kernel (radix_pipelined.cuh)  DEFAULT: persistent CTAs, every warp
-//              a worker, one shared-memory atomicAdd per key as the rank, delayed two-level
-//              decoupled look-back, double-buffered staging, coalesced scatter;
+//              a worker, one shared-memory atomicAdd per key as the rank (16-bit counters, two warps
+//              per row), delayed two-level decoupled look-back, double-buffered staging,
+//              coalesced scatter;
 //        radix_onesweep_kernel (radix_tile.cuh)  one tile per CTA; rank by MATCH / ballots /
 //              atomicOr table / atomicAdd; one- or two-level look-back; optional clusters;
 //        radix_onesweep_pipelined_kernel (radix_pipelined.cuh)  14 worker warps + 2 chain warps.
@@ -82,8 +83,9 @@ struct Variant {
       Pipelined2Shape<I, P>::kSmemBytes, radix_onesweep_pipelined2_kernel<I, 0, S, P> }
 
 const Variant kVariants[] = {
-    B200_PP2_VARIANT(18),                      //  0: DEFAULT (fastest measured): persistent CTAs, 9216-key tiles,
-                                               //     delayed two-level look-back
+    B200_PP2X_VARIANT(20, 0, 1),               //  0: DEFAULT (fastest measured, 0.712 ms/pass): persistent CTAs,
+                                               //     10240-key tiles, delayed two-level look-back, 16-bit counters
+                                               //     (two warps per row)
     B200_VARIANT(16, 18, 2, kRankAdd, 1),      //  1: 9216
     B200_VARIANT(16, 16, 2, kRankAdd, 1),      //  2: 8192
     B200_VARIANT(8, 24, 3, kRankAdd, 1),       //  3: 6144, 256 threads
@@ -134,7 +136,7 @@ const Variant kVariants[] = {
     B200_PP2X_VARIANT(18, 1, 1),                      // 47: both
     B200_PP2X_VARIANT(20, 1, 1),                      // 48: both, 10240-key tiles
     B200_PP2X_VARIANT(16, 1, 1),                      // 49: both, 8192-key tiles
-    B200_PP2X_VARIANT(20, 0, 1),                      // 50: packed counters, 10240-key tiles
+    B200_PP2_VARIANT(18),                             // 50: the default until the packed counters (0.728 ms/pass)
     B200_PP2X_VARIANT(22, 0, 1),                      // 51: 11264
     B200_PP2X_VARIANT(24, 0, 1),                      // 52: 12288
 };

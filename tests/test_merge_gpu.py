@@ -11,20 +11,29 @@ pytestmark = pytest.mark.gpu
 
 
 def test_block_sort_sorts_every_tile():
+    """Every compiled block sort (4096 / 8192-key tiles, warp-register rounds on / off)."""
     import torch
-    T = lib().b200sort_block_sort_tile()
-    for dist, n in (("uniform", 10 * T), ("edge_mix", 3 * T + 17), ("descending", T), ("uniform", 5), ("and3", 2 * T - 1)):
-        keys = datagen.make(dist, n, 6)
-        d_in = to_device(keys); d_out = torch.empty_like(d_in)
-        check(lib().b200sort_block_sort_i32(d_in.data_ptr(), d_out.data_ptr(), n, stream_ptr()))
-        torch.cuda.synchronize()
-        got = d_out.cpu().numpy()
-        for base in range(0, n, T):
-            assert_bit_exact(got[base:base + T], np.sort(keys[base:base + T]), f"{dist} tile@{base}")
-        # in place
-        check(lib().b200sort_block_sort_i32(d_in.data_ptr(), d_in.data_ptr(), n, stream_ptr()))
-        torch.cuda.synchronize()
-        assert_bit_exact(d_in.cpu().numpy(), got, "in place")
+    L = lib()
+    try:
+        for v in (0, 2, 4, 6):
+            assert L.b200sort_merge_set_variant(v) == 0
+            name = L.b200sort_merge_variant_name(v).decode()
+            T = L.b200sort_block_sort_tile()
+            for dist, n in (("uniform", 10 * T), ("edge_mix", 3 * T + 17), ("descending", T), ("uniform", 5),
+                            ("and3", 2 * T - 1), ("all_equal", 2 * T), ("lab_rand100", T + 1000)):
+                keys = datagen.make(dist, n, 6)
+                d_in = to_device(keys); d_out = torch.empty_like(d_in)
+                check(L.b200sort_block_sort_i32(d_in.data_ptr(), d_out.data_ptr(), n, stream_ptr()))
+                torch.cuda.synchronize()
+                got = d_out.cpu().numpy()
+                for base in range(0, n, T):
+                    assert_bit_exact(got[base:base + T], np.sort(keys[base:base + T]), f"{name} {dist} tile@{base}")
+                # in place
+                check(L.b200sort_block_sort_i32(d_in.data_ptr(), d_in.data_ptr(), n, stream_ptr()))
+                torch.cuda.synchronize()
+                assert_bit_exact(d_in.cpu().numpy(), got, f"{name} in place")
+    finally:
+        L.b200sort_merge_set_variant(0)
 
 
 def test_partition_points_match_cpu_merge_path_and_pass_merges():
