@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200sort_ipc_open": (_i, [_vp, ctypes.POINTER(_vp)]),
     "b200sort_ipc_close": (_i, [_vp]),
     "b200sort_order_array_host": (_i, [_vp, _sz, _i]),
+    "b200sort_host_set_streaming": (_i, [_i]),
     "b200sort_order_with_trust_host": (_i, [_vp, _sz]),
     "b200sort_host_release": (None, []),
     "b200sort_host_alloc_pinned": (_i, [ctypes.POINTER(_vp), _sz]),

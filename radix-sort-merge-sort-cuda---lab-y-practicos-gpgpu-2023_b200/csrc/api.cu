@@ -5,6 +5,7 @@
 #include "merge.cuh"
 #include "radix.cuh"
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -48,6 +49,10 @@ constexpr size_t kStageBytes = 8u << 20;       // pinned staging chunk for pagea
 constexpr size_t kDirectBytes = 4u << 20;      // below this a plain cudaMemcpy is as good as staging
 constexpr int kCopyThreads = 4;                // host threads filling / draining the staging chunks
 constexpr int kStageSlots = 2 * kCopyThreads;  // two chunks per thread: one being copied, one in DMA
+// Streamed host-array path (order_host_streamed): from this many keys on, the array is moved in
+// kStreamChunks chunks and the sort overlaps the transfers.
+constexpr size_t kStreamMinKeys = (size_t)1 << 25;
+constexpr int kStreamChunks = 8;               // a power of two
 
 struct HostArena {
     std::mutex mu;
@@ -61,6 +66,7 @@ struct HostArena {
     cudaStream_t copy_stream[kCopyThreads] = {};
     cudaEvent_t ev[kStageSlots] = {};
     cudaEvent_t ev_main = nullptr;
+    cudaEvent_t ev_step[2 * kStreamChunks] = {};   // streamed path: chunk i landed / output piece k merged
 
     void release() {
         if (d_keys) cudaFree(d_keys);
@@ -77,6 +83,7 @@ struct HostArena {
         }
         if (ev_main) cudaEventDestroy(ev_main);
         ev_main = nullptr;
+        for (auto &e : ev_step) { if (e) cudaEventDestroy(e); e = nullptr; }
         if (stream) cudaStreamDestroy(stream);
         d_keys = d_tmp = nullptr; d_ws = nullptr; stream = nullptr;
         cap_keys = cap_ws = 0; device = -1;
@@ -92,6 +99,7 @@ struct HostArena {
                 B200_CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream[i], cudaStreamNonBlocking));
             for (int i = 0; i < kStageSlots; ++i) B200_CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
             B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+            for (auto &e : ev_step) B200_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
         if (n > cap_keys) {
             if (d_keys) cudaFree(d_keys);
@@ -134,12 +142,11 @@ bool is_device_accessible_host(const void *p) {
 // own two chunks and a copy stream: while the DMA engine drains one chunk the thread fills the
 // other, so the transfer runs at PCIe speed instead of at one core's memcpy speed (what the
 // reference pays inside cudaMemcpy on a malloc'd array, SRM/lab.cu:321,397).
-int staged_copy(HostArena &a, char *dev, char *host, size_t bytes, bool to_device) {
+// `after` (may be null): an event the copy streams wait for before they touch device memory.
+int staged_copy(HostArena &a, char *dev, char *host, size_t bytes, bool to_device, cudaEvent_t after) {
     B200_TRY(a.ensure_stage());
     int dev_id = 0;
     B200_CUDA_TRY(cudaGetDevice(&dev_id));
-    // the copy streams start after everything queued on the main stream so far (e.g. the sort)
-    B200_CUDA_TRY(cudaEventRecord(a.ev_main, a.stream));
     const size_t chunks = div_up(bytes, kStageBytes);
     int status[kCopyThreads] = {};
     cudaError_t cuda_err[kCopyThreads] = {};
@@ -148,7 +155,7 @@ int staged_copy(HostArena &a, char *dev, char *host, size_t bytes, bool to_devic
         cudaError_t e = cudaSetDevice(dev_id);
         if (e != cudaSuccess) return fail(e);
         cudaStream_t cs = a.copy_stream[t];
-        if ((e = cudaStreamWaitEvent(cs, a.ev_main, 0)) != cudaSuccess) return fail(e);
+        if (after != nullptr && (e = cudaStreamWaitEvent(cs, after, 0)) != cudaSuccess) return fail(e);
         size_t k = 0;
         size_t prev_c = (size_t)-1;
         int prev_slot = 0;
@@ -197,7 +204,8 @@ int h2d(HostArena &a, int32_t *d, const int32_t *h, size_t bytes) {
         return B200SORT_OK;
     }
     // every chunk has landed when this returns, so the main stream needs no further dependency
-    return staged_copy(a, reinterpret_cast<char *>(d), reinterpret_cast<char *>(const_cast<int32_t *>(h)), bytes, true);
+    return staged_copy(a, reinterpret_cast<char *>(d), reinterpret_cast<char *>(const_cast<int32_t *>(h)), bytes, true,
+                       nullptr);
 }
 
 int d2h(HostArena &a, int32_t *h, const int32_t *d, size_t bytes) {
@@ -206,7 +214,10 @@ int d2h(HostArena &a, int32_t *h, const int32_t *d, size_t bytes) {
         B200_CUDA_TRY(cudaStreamSynchronize(a.stream));
         return B200SORT_OK;
     }
-    return staged_copy(a, reinterpret_cast<char *>(const_cast<int32_t *>(d)), reinterpret_cast<char *>(h), bytes, false);
+    // the copy streams start after everything queued on the main stream so far (the sort)
+    B200_CUDA_TRY(cudaEventRecord(a.ev_main, a.stream));
+    return staged_copy(a, reinterpret_cast<char *>(const_cast<int32_t *>(d)), reinterpret_cast<char *>(h), bytes, false,
+                       a.ev_main);
 }
 
 int sort_dispatch(int algo, const int32_t *in, int32_t *out, int32_t *t, size_t n, void *ws, size_t wsb,
@@ -229,6 +240,81 @@ size_t workspace_bytes(size_t n, int algo) {
     }
 }
 
+// Streamed host-array path for large arrays.  The transfers bound this operator (1 GiB each way over
+// PCIe against ~3 ms of sorting at n = 2^28), so the sort is arranged to hide behind them:
+//   * the array arrives in kStreamChunks chunks; chunk i is sorted (with the requested algorithm)
+//     while chunk i+1 is still on the wire;
+//   * sorted neighbours are merged as soon as both exist (merge-path passes, k4/k5'), level by
+//     level, ping-ponging between the two device buffers -- when the last chunk lands only its own
+//     sort and one merge per level are left;
+//   * the last merge is launched as kStreamChunks ranges of output tiles, and every range starts
+//     its way back to the host as soon as it is merged.
+// Level l reads runs of (chunk << l) keys from d_keys (l even) or d_tmp (l odd) and writes the other;
+// any operation on a range of keys only touches that range of the two buffers.
+std::atomic<int> g_host_streaming{1};
+
+int order_host_streamed(HostArena &a, int32_t *h_keys, size_t n, int algo) {
+    constexpr int C = kStreamChunks;
+    int levels = 0;
+    while ((1 << levels) < C) ++levels;
+    const size_t chunk = align_up(div_up(n, (size_t)C), 2 * merge_tile());
+    const size_t sort_ws = align_up(workspace_bytes(chunk, algo), 256);
+    const size_t merge_ws = merge_workspace_bytes(n);
+    B200_TRY(a.ensure(n, sort_ws + merge_ws));
+    auto *splits = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(a.d_ws) + sort_ws);
+    const bool pinned = is_device_accessible_host(h_keys);
+    cudaStream_t up = a.copy_stream[0], down = a.copy_stream[1];
+    auto buffer_of = [&](int level) { return (level & 1) ? a.d_tmp : a.d_keys; };
+
+    for (int i = 0; i < C; ++i) {
+        const size_t off = (size_t)i * chunk;
+        const size_t len = n - off < chunk ? n - off : chunk;
+        if (pinned) {
+            B200_CUDA_TRY(cudaMemcpyAsync(a.d_keys + off, h_keys + off, len * sizeof(int32_t), cudaMemcpyHostToDevice, up));
+            B200_CUDA_TRY(cudaEventRecord(a.ev_step[i], up));
+            B200_CUDA_TRY(cudaStreamWaitEvent(a.stream, a.ev_step[i], 0));
+        } else {
+            B200_TRY(staged_copy(a, reinterpret_cast<char *>(a.d_keys + off), reinterpret_cast<char *>(h_keys + off),
+                                 len * sizeof(int32_t), true, nullptr));      // returns when the chunk has landed
+        }
+        B200_TRY(sort_dispatch(algo, a.d_keys + off, a.d_keys + off, a.d_tmp + off, len, a.d_ws, sort_ws, a.stream));
+        // every level whose pair of runs is complete now, except the last one
+        for (int l = 0; l + 1 < levels && ((i + 1) & ((2 << l) - 1)) == 0; ++l) {
+            const size_t run = chunk << l;
+            const size_t start = (size_t)(i + 1 - (2 << l)) * chunk;
+            const size_t sub = n - start < 2 * run ? n - start : 2 * run;
+            B200_TRY(merge_partition(buffer_of(l) + start, sub, run, splits, a.stream));
+            B200_TRY(merge_pass(buffer_of(l) + start, buffer_of(l + 1) + start, sub, run, splits, a.stream));
+        }
+    }
+    // last level, range by range, each range followed by its copy back
+    const int32_t *src = buffer_of(levels - 1);
+    int32_t *dst = buffer_of(levels);
+    const size_t run = chunk << (levels - 1);
+    const size_t tiles = div_up(n, merge_tile());
+    const size_t per = div_up(tiles, (size_t)C);
+    B200_TRY(merge_partition(src, n, run, splits, a.stream));
+    for (int k = 0; k < C; ++k) {
+        B200_TRY(merge_pass_range(src, dst, n, run, splits, (size_t)k * per, (size_t)(k + 1) * per, a.stream));
+        B200_CUDA_TRY(cudaEventRecord(a.ev_step[C + k], a.stream));
+    }
+    for (int k = 0; k < C; ++k) {
+        const size_t e0 = (size_t)k * per * merge_tile();
+        if (e0 >= n) break;
+        const size_t e1 = (size_t)(k + 1) * per * merge_tile() < n ? (size_t)(k + 1) * per * merge_tile() : n;
+        if (pinned) {
+            B200_CUDA_TRY(cudaStreamWaitEvent(down, a.ev_step[C + k], 0));
+            B200_CUDA_TRY(cudaMemcpyAsync(h_keys + e0, dst + e0, (e1 - e0) * sizeof(int32_t), cudaMemcpyDeviceToHost, down));
+        } else {
+            B200_TRY(staged_copy(a, reinterpret_cast<char *>(dst + e0), reinterpret_cast<char *>(h_keys + e0),
+                                 (e1 - e0) * sizeof(int32_t), false, a.ev_step[C + k]));
+        }
+    }
+    if (pinned) B200_CUDA_TRY(cudaStreamSynchronize(down));
+    B200_CUDA_TRY(cudaStreamSynchronize(a.stream));
+    return B200SORT_OK;
+}
+
 int order_host(int32_t *h_keys, size_t n, int algo) {
     if (n > B200SORT_MAX_N) return B200SORT_ERR_INVALID;
     if (algo != B200SORT_ALGO_RADIX && algo != B200SORT_ALGO_MERGE && algo != B200SORT_ALGO_LAB)
@@ -238,6 +324,9 @@ int order_host(int32_t *h_keys, size_t n, int algo) {
     B200_TRY(device_check());
     HostArena &a = arena();
     std::lock_guard<std::mutex> lock(a.mu);
+    if (n >= kStreamMinKeys && g_host_streaming.load() != 0) {
+        return order_host_streamed(a, h_keys, n, algo);
+    }
     const size_t wsb = workspace_bytes(n, algo);
     B200_TRY(a.ensure(n, wsb));
     const size_t bytes = n * sizeof(int32_t);
@@ -357,6 +446,7 @@ unsigned long long b200sort_launch_count(void) { return g_launch_count; }
 void b200sort_launch_count_reset(void) { g_launch_count = 0; }
 
 int b200sort_order_array_host(int32_t *h_keys, size_t n, int algo) { return order_host(h_keys, n, algo); }
+int b200sort_host_set_streaming(int enabled) { g_host_streaming.store(enabled ? 1 : 0); return B200SORT_OK; }
 int b200sort_order_with_trust_host(int32_t *h_keys, size_t n) {
     return order_host(h_keys, n, B200SORT_ALGO_MERGE);
 }

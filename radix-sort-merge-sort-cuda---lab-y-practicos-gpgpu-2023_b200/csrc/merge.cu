@@ -350,11 +350,11 @@ __device__ __forceinline__ MergeTileGeom merge_tile_geom(const int32_t *in, size
 
 __global__ void __launch_bounds__(kSortThreads, 4)
 merge_pass_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, size_t n, size_t run,
-                  const uint32_t *__restrict__ splits, size_t tiles)
+                  const uint32_t *__restrict__ splits, size_t t_begin, size_t tiles /* = end of the range */)
 {
     __shared__ int32_t s[kSortSmemWords];
     const uint32_t tid = threadIdx.x;
-    size_t t = blockIdx.x;
+    size_t t = t_begin + blockIdx.x;
     if (t >= tiles) return;
 
     int32_t next_keys[kSortK];
@@ -491,11 +491,12 @@ __device__ __forceinline__ MergeTileGeom32 merge_tile_geom32(const int32_t *in, 
 
 __global__ void __launch_bounds__(kSortThreads, 4)
 merge_pass2_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, size_t n, size_t run,
-                   int pair_shift, const uint32_t *__restrict__ splits, size_t tiles)
+                   int pair_shift, const uint32_t *__restrict__ splits, size_t t_begin,
+                   size_t tiles /* = end of the range */)
 {
     __shared__ int32_t s2[2][kPass2Words];
     const uint32_t tid = threadIdx.x;
-    size_t t = blockIdx.x;
+    size_t t = t_begin + blockIdx.x;
     if (t >= tiles) return;
     const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
     const uint32_t padtid = pad(tid);
@@ -620,23 +621,31 @@ int merge_partition(const int32_t *d_in, size_t n, size_t run, uint32_t *d_split
     return B200SORT_OK;
 }
 
-int merge_pass(const int32_t *d_in, int32_t *d_out, size_t n, size_t run, const uint32_t *d_splits,
-               cudaStream_t s) {
+int merge_pass_range(const int32_t *d_in, int32_t *d_out, size_t n, size_t run, const uint32_t *d_splits,
+                     size_t tile_begin, size_t tile_end, cudaStream_t s) {
     if (n == 0) return B200SORT_OK;
     if (run == 0 || run % kSortTile != 0) return B200SORT_ERR_INVALID;
     const size_t tiles = div_up(n, kSortTile);
+    if (tile_end > tiles) tile_end = tiles;
+    if (tile_begin >= tile_end) return B200SORT_OK;
+    const size_t count = tile_end - tile_begin;
     const size_t slots = (size_t)kNumSMs * 4;              // persistent: 4 CTAs of 256 threads per SM
-    const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
+    const unsigned grid = (unsigned)(count < slots ? count : slots);
     if ((g_merge_variant.load() & 1) == 0)
     {
         int pair_shift = -1;                                   // 2 * run a power of two: shifts instead of divisions
         if ((run & (run - 1)) == 0) { pair_shift = 1; while (((size_t)1 << pair_shift) < 2 * run) ++pair_shift; }
-        merge_pass2_kernel<<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tiles);
+        merge_pass2_kernel<<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tile_begin, tile_end);
     }
     else
-        merge_pass_kernel<<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, d_splits, tiles);
+        merge_pass_kernel<<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, d_splits, tile_begin, tile_end);
     B200_LAUNCH_CHECK();
     return B200SORT_OK;
+}
+
+int merge_pass(const int32_t *d_in, int32_t *d_out, size_t n, size_t run, const uint32_t *d_splits,
+               cudaStream_t s) {
+    return merge_pass_range(d_in, d_out, n, run, d_splits, 0, div_up(n, kSortTile), s);
 }
 
 int merge_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, void *d_ws,

@@ -35,6 +35,34 @@ def test_host_operator_with_pinned_memory():
     assert_bit_exact(a, oracle.radix_sort(keys), "pinned")
 
 
+@pytest.mark.parametrize("n", [1 << 25, (1 << 25) + 12345, 3 * (1 << 24) + 77])
+def test_streamed_host_operator_large_arrays(n):
+    """From 2^25 keys on the host-array operator streams (chunked H2D, chunk sorts, progressive
+    merge-path merges, output ranges copied back as they are merged).  Pageable and pinned arrays,
+    radix and merge, and the one-shot path on the same input: all the same bytes as the oracle."""
+    import torch
+    from b200sort._lib import ALGO_MERGE, ALGO_RADIX, check
+    L = b200sort.lib()
+    keys = datagen.uniform(n, 41)
+    keys[: n // 16] = np.iinfo(np.int32).max               # sentinel-valued keys in quantity
+    keys[n // 3: n // 3 + 100000] = -7                     # a long run of equal keys across a chunk boundary
+    want = oracle.radix_sort(keys)
+    try:
+        for algo in (ALGO_RADIX, ALGO_MERGE):
+            a = keys.copy()
+            check(L.b200sort_order_array_host(a.ctypes.data, n, algo))
+            assert_bit_exact(a, want, f"pageable algo={algo}")
+        pinned = torch.from_numpy(keys.copy()).pin_memory().numpy()
+        check(L.b200sort_order_array_host(pinned.ctypes.data, n, ALGO_RADIX))
+        assert_bit_exact(pinned, want, "pinned")
+        L.b200sort_host_set_streaming(0)
+        a = keys.copy()
+        check(L.b200sort_order_array_host(a.ctypes.data, n, ALGO_RADIX))
+        assert_bit_exact(a, want, "one-shot")
+    finally:
+        L.b200sort_host_set_streaming(1)
+
+
 def test_cxx_symbols_sort_in_place_like_the_reference_header_says():
     L = b200sort.lib()
     for sym in ("_Z11order_arrayPii", "_Z16order_with_trustPii"):
