@@ -153,7 +153,7 @@ void               b200sort_launch_count_reset(void);
  * per-process device arena (keys, scratch, workspace, pinned staging) that grows on demand and is
  * reused across calls; b200sort_host_release frees it.  h_keys may be pageable or pinned. */
 int  b200sort_order_array_host(int32_t *h_keys, size_t n, int algo);
-/* From 2^25 keys on the operator streams: the array moves in 8 chunks, each chunk is sorted while the
+/* From 2^25 keys on, for pinned (device-accessible) arrays, the operator streams: the array moves in 8 chunks, each chunk is sorted while the
  * next one is on the wire, sorted neighbours are merged (merge-path passes) as soon as both exist, and
  * the last merge hands finished output ranges to the copy back.  0 switches that off (one H2D, one
  * sort, one D2H); 1 = default.  Same result either way. */

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -47,8 +48,22 @@ int check_sort_args(const void *keys, const void *tmp, size_t n) {
 // ---- the per-process arena behind the host-array operator ---------------------------------------
 constexpr size_t kStageBytes = 8u << 20;       // pinned staging chunk for pageable callers
 constexpr size_t kDirectBytes = 4u << 20;      // below this a plain cudaMemcpy is as good as staging
-constexpr int kCopyThreads = 4;                // host threads filling / draining the staging chunks
+constexpr int kCopyThreads = 16;               // most host threads ever filling / draining the staging chunks
 constexpr int kStageSlots = 2 * kCopyThreads;  // two chunks per thread: one being copied, one in DMA
+// How many of them a transfer uses: B200SORT_COPY_THREADS (1..16), else one per host core up to 16.
+// Measured on the B200 box (16 cores), pageable array of 2^28 keys through order_array (ms):
+// 2 threads 115, 4: 76, 8: 72, 12: 62, 16: 54 (profiles/r01_host_copy_threads.txt); the two
+// transfers alone take 40 ms from pinned memory.
+int copy_threads() {
+    static const int n = [] {
+        const char *e = getenv("B200SORT_COPY_THREADS");
+        const int v = e ? atoi(e) : 0;
+        if (v >= 1 && v <= kCopyThreads) return v;
+        const unsigned hw = std::thread::hardware_concurrency();
+        return (int)(hw < 1 ? 4 : hw > (unsigned)kCopyThreads ? (unsigned)kCopyThreads : hw);
+    }();
+    return n;
+}
 // Streamed host-array path (order_host_streamed): from this many keys on, the array is moved in
 // kStreamChunks chunks and the sort overlaps the transfers.
 constexpr size_t kStreamMinKeys = (size_t)1 << 25;
@@ -121,7 +136,7 @@ struct HostArena {
     }
 
     int ensure_stage() {
-        for (int i = 0; i < kStageSlots; ++i)
+        for (int i = 0; i < 2 * copy_threads(); ++i)
             if (h_stage[i] == nullptr) B200_CUDA_TRY(cudaMallocHost(&h_stage[i], kStageBytes));
         return B200SORT_OK;
     }
@@ -148,6 +163,7 @@ int staged_copy(HostArena &a, char *dev, char *host, size_t bytes, bool to_devic
     int dev_id = 0;
     B200_CUDA_TRY(cudaGetDevice(&dev_id));
     const size_t chunks = div_up(bytes, kStageBytes);
+    const int nthreads = copy_threads();
     int status[kCopyThreads] = {};
     cudaError_t cuda_err[kCopyThreads] = {};
     auto worker = [&](int t) {
@@ -159,7 +175,7 @@ int staged_copy(HostArena &a, char *dev, char *host, size_t bytes, bool to_devic
         size_t k = 0;
         size_t prev_c = (size_t)-1;
         int prev_slot = 0;
-        for (size_t c = t; c < chunks; c += kCopyThreads, ++k) {
+        for (size_t c = t; c < chunks; c += nthreads, ++k) {
             const int slot = 2 * t + (int)(k & 1);
             const size_t off = c * kStageBytes;
             const size_t len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
@@ -190,10 +206,10 @@ int staged_copy(HostArena &a, char *dev, char *host, size_t bytes, bool to_devic
         if (to_device && (e = cudaStreamSynchronize(cs)) != cudaSuccess) return fail(e);
     };
     std::vector<std::thread> pool;
-    for (int t = 1; t < kCopyThreads; ++t) pool.emplace_back(worker, t);
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker, t);
     worker(0);
     for (auto &th : pool) th.join();
-    for (int t = 0; t < kCopyThreads; ++t)
+    for (int t = 0; t < nthreads; ++t)
         if (status[t] != B200SORT_OK) return record_cuda(cuda_err[t]);
     return B200SORT_OK;
 }
@@ -240,7 +256,7 @@ size_t workspace_bytes(size_t n, int algo) {
     }
 }
 
-// Streamed host-array path for large arrays.  The transfers bound this operator (1 GiB each way over
+// Streamed host-array path for large device-accessible (pinned / managed) arrays.  The transfers bound this operator (1 GiB each way over
 // PCIe against ~3 ms of sorting at n = 2^28), so the sort is arranged to hide behind them:
 //   * the array arrives in kStreamChunks chunks; chunk i is sorted (with the requested algorithm)
 //     while chunk i+1 is still on the wire;
@@ -262,21 +278,15 @@ int order_host_streamed(HostArena &a, int32_t *h_keys, size_t n, int algo) {
     const size_t merge_ws = merge_workspace_bytes(n);
     B200_TRY(a.ensure(n, sort_ws + merge_ws));
     auto *splits = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(a.d_ws) + sort_ws);
-    const bool pinned = is_device_accessible_host(h_keys);
     cudaStream_t up = a.copy_stream[0], down = a.copy_stream[1];
     auto buffer_of = [&](int level) { return (level & 1) ? a.d_tmp : a.d_keys; };
 
     for (int i = 0; i < C; ++i) {
         const size_t off = (size_t)i * chunk;
         const size_t len = n - off < chunk ? n - off : chunk;
-        if (pinned) {
-            B200_CUDA_TRY(cudaMemcpyAsync(a.d_keys + off, h_keys + off, len * sizeof(int32_t), cudaMemcpyHostToDevice, up));
-            B200_CUDA_TRY(cudaEventRecord(a.ev_step[i], up));
-            B200_CUDA_TRY(cudaStreamWaitEvent(a.stream, a.ev_step[i], 0));
-        } else {
-            B200_TRY(staged_copy(a, reinterpret_cast<char *>(a.d_keys + off), reinterpret_cast<char *>(h_keys + off),
-                                 len * sizeof(int32_t), true, nullptr));      // returns when the chunk has landed
-        }
+        B200_CUDA_TRY(cudaMemcpyAsync(a.d_keys + off, h_keys + off, len * sizeof(int32_t), cudaMemcpyHostToDevice, up));
+        B200_CUDA_TRY(cudaEventRecord(a.ev_step[i], up));
+        B200_CUDA_TRY(cudaStreamWaitEvent(a.stream, a.ev_step[i], 0));
         B200_TRY(sort_dispatch(algo, a.d_keys + off, a.d_keys + off, a.d_tmp + off, len, a.d_ws, sort_ws, a.stream));
         // every level whose pair of runs is complete now, except the last one
         for (int l = 0; l + 1 < levels && ((i + 1) & ((2 << l) - 1)) == 0; ++l) {
@@ -302,15 +312,10 @@ int order_host_streamed(HostArena &a, int32_t *h_keys, size_t n, int algo) {
         const size_t e0 = (size_t)k * per * merge_tile();
         if (e0 >= n) break;
         const size_t e1 = (size_t)(k + 1) * per * merge_tile() < n ? (size_t)(k + 1) * per * merge_tile() : n;
-        if (pinned) {
-            B200_CUDA_TRY(cudaStreamWaitEvent(down, a.ev_step[C + k], 0));
-            B200_CUDA_TRY(cudaMemcpyAsync(h_keys + e0, dst + e0, (e1 - e0) * sizeof(int32_t), cudaMemcpyDeviceToHost, down));
-        } else {
-            B200_TRY(staged_copy(a, reinterpret_cast<char *>(dst + e0), reinterpret_cast<char *>(h_keys + e0),
-                                 (e1 - e0) * sizeof(int32_t), false, a.ev_step[C + k]));
-        }
+        B200_CUDA_TRY(cudaStreamWaitEvent(down, a.ev_step[C + k], 0));
+        B200_CUDA_TRY(cudaMemcpyAsync(h_keys + e0, dst + e0, (e1 - e0) * sizeof(int32_t), cudaMemcpyDeviceToHost, down));
     }
-    if (pinned) B200_CUDA_TRY(cudaStreamSynchronize(down));
+    B200_CUDA_TRY(cudaStreamSynchronize(down));
     B200_CUDA_TRY(cudaStreamSynchronize(a.stream));
     return B200SORT_OK;
 }
@@ -324,9 +329,11 @@ int order_host(int32_t *h_keys, size_t n, int algo) {
     B200_TRY(device_check());
     HostArena &a = arena();
     std::lock_guard<std::mutex> lock(a.mu);
-    if (n >= kStreamMinKeys && g_host_streaming.load() != 0) {
+    // Pageable arrays move through the staging chunks at the host's memcpy speed; cutting that
+    // pipeline into eight short ones costs more than the hidden sort saves (measured: 20.2 ms
+    // streamed against 12.9 ms in one go at n = 2^25), so only device-accessible arrays stream.
+    if (n >= kStreamMinKeys && g_host_streaming.load() != 0 && is_device_accessible_host(h_keys))
         return order_host_streamed(a, h_keys, n, algo);
-    }
     const size_t wsb = workspace_bytes(n, algo);
     B200_TRY(a.ensure(n, wsb));
     const size_t bytes = n * sizeof(int32_t);
