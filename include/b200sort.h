@@ -76,6 +76,18 @@ int    b200sort_radix_i32(int32_t *d_keys, int32_t *d_tmp, size_t n,
                           void *d_ws, size_t ws_bytes, void *stream);
 int    b200sort_merge_i32(int32_t *d_keys, int32_t *d_tmp, size_t n,
                           void *d_ws, size_t ws_bytes, void *stream);
+/* Sort-by-key: (key, 32-bit value) pairs ordered by key, ascending signed, STABLE --
+ * equal keys keep their input order, the A-before-B tie rule of SRM/lab.cu:163-170 carried through the
+ * whole sort; with values 0..n-1 the result is the index permutation the doc comment at
+ * SRM/lab.cu:44-45 ("positions") had in mind.  The onesweep passes with the value riding beside the key
+ * (16 B/key per pass).  Workspace: b200sort_workspace_bytes(n, B200SORT_ALGO_RADIX).  The _copy form
+ * leaves the inputs untouched.  Needs the lane-ordered atomics (b200sort_radix_atomic_order_ok() == 1);
+ * returns B200SORT_ERR_INVALID otherwise. */
+int    b200sort_radix_pairs_i32(int32_t *d_keys, int32_t *d_vals, int32_t *d_tmp_keys, int32_t *d_tmp_vals,
+                                size_t n, void *d_ws, size_t ws_bytes, void *stream);
+int    b200sort_radix_pairs_copy_i32(const int32_t *d_keys_in, const int32_t *d_vals_in, int32_t *d_keys_out,
+                                     int32_t *d_vals_out, int32_t *d_tmp_keys, int32_t *d_tmp_vals, size_t n,
+                                     void *d_ws, size_t ws_bytes, void *stream);
 /* The assignment's staged pipeline (SRM/letra.pdf p.3 parts a-d, SRM/lab.cu:303-402) as a third
  * algorithm: 1-bit warp split on 32-key groups -> in-block rank merges -> merge-path merges. */
 int    b200sort_lab_i32(int32_t *d_keys, int32_t *d_tmp, size_t n,

@@ -122,6 +122,17 @@ def radix_pass(keys, digit_pass: int) -> np.ndarray:
     return out
 
 
+def sort_pairs(keys, vals) -> tuple[np.ndarray, np.ndarray]:
+    """(key, value) pairs ordered by key, ascending signed, STABLE: equal keys keep their input order.
+    That is the reference's tie rule (A's equal elements before B's, SRM/lab.cu:163-170) applied at every
+    merge level of SRM/lab.cu:303-402, i.e. what carrying the "positions" array of the doc comment at
+    SRM/lab.cu:44-45 through the lab pipeline would return.  numpy's stable argsort states it directly."""
+    k, v = _i32(keys), _i32(vals)
+    assert k.shape == v.shape
+    order = np.argsort(k, kind="stable")
+    return k[order], v[order]
+
+
 def merge_path(a, b, diag: int) -> int:
     a, b = _i32(a), _i32(b)
     return int(_lib.oracle_merge_path(a.ctypes.data, a.size, b.ctypes.data, b.size, int(diag)))

@@ -37,6 +37,8 @@ SIGNATURES = {
     "b200sort_workspace_bytes": (_sz, [_sz, _i]),
     "b200sort_radix_i32": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "b200sort_merge_i32": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "b200sort_radix_pairs_i32": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "b200sort_radix_pairs_copy_i32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "b200sort_lab_i32": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "b200sort_lab_tile_sort_i32": (_i, [_vp, _vp, _sz, _vp]),
     "b200sort_sort_i32": (_i, [_i, _vp, _vp, _sz, _vp, _sz, _vp]),

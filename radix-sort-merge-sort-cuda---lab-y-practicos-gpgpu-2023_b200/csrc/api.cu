@@ -376,6 +376,24 @@ int b200sort_radix_i32(int32_t *d_keys, int32_t *d_tmp, size_t n, void *d_ws, si
     return radix_sort(d_keys, d_keys, d_tmp, n, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int b200sort_radix_pairs_i32(int32_t *d_keys, int32_t *d_vals, int32_t *d_tmp_keys, int32_t *d_tmp_vals, size_t n,
+                             void *d_ws, size_t ws_bytes, void *stream) {
+    B200_TRY(check_sort_args(d_keys, d_tmp_keys, n));
+    B200_TRY(check_sort_args(d_vals, d_tmp_vals, n));
+    return radix_sort_pairs(d_keys, d_keys, d_tmp_keys, d_vals, d_vals, d_tmp_vals, n, d_ws, ws_bytes,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int b200sort_radix_pairs_copy_i32(const int32_t *d_keys_in, const int32_t *d_vals_in, int32_t *d_keys_out,
+                                  int32_t *d_vals_out, int32_t *d_tmp_keys, int32_t *d_tmp_vals, size_t n,
+                                  void *d_ws, size_t ws_bytes, void *stream) {
+    B200_TRY(check_sort_args(d_keys_out, d_tmp_keys, n));
+    B200_TRY(check_sort_args(d_vals_out, d_tmp_vals, n));
+    if (n > 0 && (d_keys_in == nullptr || d_vals_in == nullptr)) return B200SORT_ERR_INVALID;
+    return radix_sort_pairs(d_keys_in, d_keys_out, d_tmp_keys, d_vals_in, d_vals_out, d_tmp_vals, n, d_ws, ws_bytes,
+                            static_cast<cudaStream_t>(stream));
+}
+
 int b200sort_merge_i32(int32_t *d_keys, int32_t *d_tmp, size_t n, void *d_ws, size_t ws_bytes, void *stream) {
     B200_TRY(check_sort_args(d_keys, d_tmp, n));
     return merge_sort(d_keys, d_keys, d_tmp, n, d_ws, ws_bytes, static_cast<cudaStream_t>(stream), nullptr);

@@ -79,7 +79,7 @@ struct Variant {
       Pipelined2Shape<I>::kTile, Pipelined2Shape<I>::kSmemBytes, radix_onesweep_pipelined2_kernel<I> }
 
 #define B200_PP2X_VARIANT(I, S, P)                                                                  \
-    { "pipelined2_16w_ipt" #I "_split" #S "_pack" #P, kRankAdd, 0, 1, 512, Pipelined2Shape<I, P>::kTile, \
+    { "pipelined2_16w_ipt" #I "_kRankAdd_split" #S "_pack" #P, kRankAdd, 0, 1, 512, Pipelined2Shape<I, P>::kTile, \
       Pipelined2Shape<I, P>::kSmemBytes, radix_onesweep_pipelined2_kernel<I, 0, S, P> }
 
 const Variant kVariants[] = {
@@ -385,6 +385,67 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
 int radix_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, void *d_ws,
                size_t ws_bytes, cudaStream_t s) {
     return radix_sort_impl(d_in, d_out, d_tmp, n, d_ws, ws_bytes, s, nullptr);
+}
+
+// ---- sort-by-key ----------------------------------------------------------------
+// The same four stable passes with a 32-bit value carried beside every key: 16 B/key per pass.
+// One shape only: the packed-counter persistent kernel with 512 x 10 = 5120-key tiles (the values
+// take the registers and the shared memory the larger key-only tile uses).  Stable, because every
+// pass is (that is what makes LSD correct in the first place): equal keys keep their input order,
+// the A-before-B rule of SRM/lab.cu:163-170 carried through the whole sort.
+constexpr int kPairsIPT = 10;
+size_t radix_pairs_tile() { return Pipelined2Shape<kPairsIPT, 1, 1>::kTile; }
+
+int radix_sort_pairs(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const int32_t *v_in, int32_t *v_out,
+                     int32_t *v_tmp, size_t n, void *d_ws, size_t ws_bytes, cudaStream_t s) {
+    if (n == 0) return B200SORT_OK;
+    if (n == 1) {
+        if (d_in != d_out) B200_CUDA_TRY(cudaMemcpyAsync(d_out, d_in, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        if (v_in != v_out) B200_CUDA_TRY(cudaMemcpyAsync(v_out, v_in, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        return B200SORT_OK;
+    }
+    if ((d_in == d_out) != (v_in == v_out)) return B200SORT_ERR_INVALID;   // the plan is shared by keys and values
+    B200_TRY(check_ws(d_ws, ws_bytes, n));
+    if (!atomic_order_ok()) return B200SORT_ERR_INVALID;                   // no ballot-ranked pairs shape is compiled
+    static std::atomic<bool> attr_set{false};
+    constexpr size_t smem = Pipelined2Shape<kPairsIPT, 1, 1>::kSmemBytes;
+    if (!attr_set.load(std::memory_order_acquire)) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_onesweep_pairs_kernel<kPairsIPT>),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set.store(true, std::memory_order_release);
+    }
+    B200_TRY(ensure_hist_attr());
+    auto *ctl = static_cast<RadixControl *>(d_ws);
+    const size_t tiles = div_up(n, radix_pairs_tile());
+    const size_t rows = tiles + div_up(tiles, (size_t)kLookGroup);
+    uint32_t *status[2];
+    status[0] = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(d_ws) + kRadixControlBytes);
+    status[1] = status[0] + rows * kRadixBins;
+    const int skip = g_skip_enabled.load();
+    const uint32_t in_place = (d_in == d_out) ? 1u : 0u;
+
+    B200_CUDA_TRY(cudaMemsetAsync(ctl, 0, kRadixZeroBytes, s));
+    radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_in, n, ctl, status[0], rows * kRadixBins,
+                                                                 (uint32_t)skip, in_place);
+    B200_LAUNCH_CHECK();
+    const unsigned slots = 2u * kNumSMs;
+    const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
+    for (int pass = 0; pass < kRadixPasses; ++pass) {
+        uint32_t *cur = status[pass & 1];
+        uint32_t *next = (pass + 1 < kRadixPasses) ? status[(pass + 1) & 1] : nullptr;
+        radix_onesweep_pairs_kernel<kPairsIPT><<<grid, 512, smem, s>>>(d_in, d_out, d_tmp, n, pass, ctl, cur, next, 1,
+                                                                      v_in, v_out, v_tmp);
+        B200_LAUNCH_CHECK();
+    }
+    if (skip) {
+        const size_t blocks = div_up(div_up(n, 4), 256);
+        const unsigned g2 = (unsigned)(blocks < (size_t)kNumSMs * 8 ? blocks : (size_t)kNumSMs * 8);
+        radix_final_copy_kernel<<<g2, 256, 0, s>>>(d_in, d_out, d_tmp, n, ctl);
+        B200_LAUNCH_CHECK();
+        radix_final_copy_kernel<<<g2, 256, 0, s>>>(v_in, v_out, v_tmp, n, ctl);
+        B200_LAUNCH_CHECK();
+    }
+    return B200SORT_OK;
 }
 
 int radix_sort_timed(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, void *d_ws,

@@ -41,6 +41,10 @@ int radix_single_pass(const int32_t *d_in, int32_t *d_out, size_t n, int pass,
 // d_in may equal d_out (in-place sort); otherwise d_in is left untouched.
 int radix_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, void *d_ws,
                size_t ws_bytes, cudaStream_t s);
+// Sort-by-key: (key, value) pairs ordered by key, stable.  Same workspace as radix_sort.  Either both of
+// d_in == d_out and v_in == v_out (in place) or neither.
+int radix_sort_pairs(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const int32_t *v_in, int32_t *v_out,
+                     int32_t *v_tmp, size_t n, void *d_ws, size_t ws_bytes, cudaStream_t s);
 // Same, with CUDA events around every kernel: ms[0] histogram, ms[1..4] passes, ms[5] final copy.
 int radix_sort_timed(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, void *d_ws,
                      size_t ws_bytes, cudaStream_t s, float *ms);

@@ -348,27 +348,29 @@ radix_onesweep_pipelined_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t
 // SPLIT: the previous tile's two look-back walks run concurrently, one per thread group (see below).
 // PACK : two warps share one row of digit counters, 16 bits each (8 rows instead of 16): half the
 //        shared-memory traffic of the digit phase and of the zeroing.
-template <int IPT, int PACK = 0>
+// KV   : every key carries a 32-bit value through the pass (sort-by-key): the
+//        values are loaded, staged and written beside the keys, so the staging area doubles.
+template <int IPT, int PACK = 0, int KV = 0>
 struct Pipelined2Shape {
     static constexpr int kThreads = 512;
     static constexpr int kTile = kThreads * IPT;
     static constexpr int kRows = PACK ? 8 : 16;
     static constexpr size_t kSmemBytes =
         (size_t)kRows * kRadixBins * 4              // per-warp digit counters -> positions
-        + (size_t)2 * kTile * 4                     // two staging buffers
+        + (size_t)(KV ? 4 : 2) * kTile * 4          // two staging buffers (keys; KV: and two for the values)
         + (size_t)(2 + 1 + 2 + 1) * kRadixBins * 4  // gofs[2], total, tstart[2], previous tile's group prefix
         + 128;
 };
 
-template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0>
-__global__ void __launch_bounds__(512, 2)
-radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
-                                 int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
-                                 int follow_plan)
+template <int IPT, int TIMING, int SPLIT, int PACK, int KV>
+__device__ __forceinline__ void
+radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
+                               int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
+                               int follow_plan, const int32_t *in_vals, int32_t *out_vals, int32_t *tmp_vals)
 {
     constexpr int kThreads = 512;
-    constexpr int kTile = Pipelined2Shape<IPT, PACK>::kTile;
-    constexpr int kRows = Pipelined2Shape<IPT, PACK>::kRows;
+    constexpr int kTile = Pipelined2Shape<IPT, PACK, KV>::kTile;
+    constexpr int kRows = Pipelined2Shape<IPT, PACK, KV>::kRows;
     constexpr int W = 8;                                      // status rows in flight per thread
     static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in pairs");
     static_assert(kTile + 64 < 65536, "PACK keeps 16-bit positions");
@@ -376,7 +378,8 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *s_table  = reinterpret_cast<uint32_t *>(smem_raw);                      // [kRows][256]
     int32_t  *s_keys   = reinterpret_cast<int32_t *>(s_table + kRows * kRadixBins);   // [2][kTile]
-    uint32_t *s_gofs   = reinterpret_cast<uint32_t *>(s_keys + 2 * kTile);            // [2][256]
+    int32_t  *s_vals   = s_keys + 2 * kTile;                                          // KV: [2][kTile]
+    uint32_t *s_gofs   = reinterpret_cast<uint32_t *>(s_keys + (KV ? 4 : 2) * kTile); // [2][256]
     uint32_t *s_total  = s_gofs + 2 * kRadixBins;                                     // [256]
     uint32_t *s_tstart = s_total + kRadixBins;                                        // [2][256]
     uint32_t *s_g2     = s_tstart + 2 * kRadixBins;           // [256] SPLIT: previous tile's prefix over earlier groups
@@ -387,6 +390,8 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
 
     const int32_t *in = in_buf;
     int32_t *out = out_buf;
+    const int32_t *vin = in_vals;
+    int32_t *vout = out_vals;
     if (follow_plan) {
         if (ctl->skip[pass]) {
             const size_t rows = tiles + (tiles + kLookGroup - 1) / kLookGroup;
@@ -398,6 +403,10 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
         const uint32_t ss = ctl->src_sel[pass], ds = ctl->dst_sel[pass];
         in = (ss == kSelIn) ? in_buf : (ss == kSelTmp) ? tmp_buf : out_buf;
         out = (ds == kSelTmp) ? tmp_buf : out_buf;
+        if (KV) {                                             // the values follow the keys' plan
+            vin = (ss == kSelIn) ? in_vals : (ss == kSelTmp) ? tmp_vals : out_vals;
+            vout = (ds == kSelTmp) ? tmp_vals : out_vals;
+        }
     }
     const int shift = pass * kRadixBits;
     const uint32_t flip = (pass == kRadixPasses - 1) ? 0x80u : 0u;
@@ -422,6 +431,7 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
     auto pair_bar = [&]() { bar_sync(3 + (warp >> 1), 64); };     // the two warps that share a counter row
 
     int32_t key[IPT];
+    int32_t val[KV ? IPT : 1];
     auto load_tile = [&](uint32_t t) {
         const size_t tile_base = (size_t)t * kTile;
         const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
@@ -434,18 +444,27 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
             for (int i = 0; i < IPT; ++i)
                 key[i] = (wofs + i * 32 < valid) ? ld_stream(src + i * 32) : 0x7FFFFFFF;
         }
+        if (KV) {
+            const int32_t *vsrc = vin + tile_base + wofs;
+#pragma unroll
+            for (int i = 0; i < (KV ? IPT : 0); ++i)
+                val[i] = (wofs + i * 32 < valid) ? ld_stream(vsrc + i * 32) : 0;
+        }
     };
     auto write_tile = [&](uint32_t t, int buf) {
         const size_t tile_base = (size_t)t * kTile;
         const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
         const int32_t *sk = s_keys + buf * kTile;
+        const int32_t *sv = s_vals + buf * kTile;
         const uint32_t *go = s_gofs + buf * kRadixBins;
         if (valid == (uint32_t)kTile) {
 #pragma unroll
             for (int j = 0; j < IPT; ++j) {
                 const uint32_t p = tid + j * kThreads;
                 const int32_t k = sk[p];
-                st_stream(out + (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p), k);
+                const size_t dst = (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p);
+                st_stream(out + dst, k);
+                if (KV) st_stream(vout + dst, sv[p]);
             }
         } else {
 #pragma unroll
@@ -453,7 +472,9 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
                 const uint32_t p = tid + j * kThreads;
                 if (p < valid) {
                     const int32_t k = sk[p];
-                    st_stream(out + (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p), k);
+                    const size_t dst = (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p);
+                    st_stream(out + dst, k);
+                    if (KV) st_stream(vout + dst, sv[p]);
                 }
             }
         }
@@ -674,10 +695,13 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
         // ---- stage this tile's keys in digit order ----------------------------------------------------
         {
             int32_t *sk = s_keys + b * kTile;
+            int32_t *sv = s_vals + b * kTile;
 #pragma unroll
             for (int i = 0; i < IPT; ++i) {
                 const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
-                sk[my_half(wt[digit_of(key[i], shift, flip)]) + r] = key[i];
+                const uint32_t pos = my_half(wt[digit_of(key[i], shift, flip)]) + r;
+                sk[pos] = key[i];
+                if (KV) sv[pos] = val[KV ? i : 0];
             }
         }
         // the counters are cleared for the next tile once nobody reads positions from them any more
@@ -717,5 +741,25 @@ radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_
     }
 }
 
+template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0>
+__global__ void __launch_bounds__(512, 2)
+radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
+                                 int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
+                                 int follow_plan)
+{
+    radix_onesweep_pipelined2_body<IPT, TIMING, SPLIT, PACK, 0>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
+                                                                status_next, follow_plan, nullptr, nullptr, nullptr);
+}
+
+// Sort-by-key: the same pass with a 32-bit value riding along with every key.
+template <int IPT>
+__global__ void __launch_bounds__(512, 2)
+radix_onesweep_pairs_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
+                            int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
+                            int follow_plan, const int32_t *in_vals, int32_t *out_vals, int32_t *tmp_vals)
+{
+    radix_onesweep_pipelined2_body<IPT, 0, 0, 1, 1>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
+                                                    status_next, follow_plan, in_vals, out_vals, tmp_vals);
+}
 
 }  // namespace b200sort

@@ -106,3 +106,30 @@ def test_stage_helpers_against_numpy():
     assert oracle.is_sorted(merged) and not oracle.is_sorted(keys)
     assert oracle.multiset_fingerprint(keys) == oracle.multiset_fingerprint(np.sort(keys))
     assert oracle.multiset_fingerprint(keys) != oracle.multiset_fingerprint(keys + 1)
+
+
+def test_sort_pairs_is_the_stable_order_the_rank_merge_tie_rule_gives():
+    """oracle.sort_pairs against an independent statement: merge sort by rank_merge's tie rule (equal keys
+    of the left run first, SRM/lab.cu:163-170) on keys tagged with their input position."""
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 33, 1000, 4097):
+        keys = rng.integers(-5, 5, n).astype(np.int32)                 # many ties
+        vals = np.arange(n, dtype=np.int32)
+        got_k, got_v = oracle.sort_pairs(keys, vals)
+        # independent: bottom-up merges, ties take from the left run
+        runs = [[(int(k), int(v))] for k, v in zip(keys, vals)]
+        while len(runs) > 1:
+            nxt = []
+            for i in range(0, len(runs), 2):
+                if i + 1 == len(runs):
+                    nxt.append(runs[i]); continue
+                a, b, out, x, y = runs[i], runs[i + 1], [], 0, 0
+                while x < len(a) or y < len(b):
+                    if y == len(b) or (x < len(a) and a[x][0] <= b[y][0]):
+                        out.append(a[x]); x += 1
+                    else:
+                        out.append(b[y]); y += 1
+                nxt.append(out)
+            runs = nxt
+        assert [p[0] for p in runs[0]] == got_k.tolist() and [p[1] for p in runs[0]] == got_v.tolist()
+        assert got_k.tobytes() == oracle.radix_sort(keys).tobytes()

@@ -75,6 +75,64 @@ def test_radix_sort_all_tile_shapes():
         L.b200sort_radix_set_variant(0)
 
 
+def _gpu_sort_pairs(keys, vals, copy_form=False):
+    import torch
+    L = lib()
+    n = keys.size
+    dk, dv = to_device(keys), to_device(vals)
+    tk = torch.empty(max(n, 1), dtype=torch.int32, device="cuda"); tv = torch.empty_like(tk)
+    ws, ptr, nbytes = workspace(n, ALGO_RADIX)
+    if copy_form:
+        ok = torch.full((max(n, 1),), -1, dtype=torch.int32, device="cuda"); ov = torch.full_like(ok, -1)
+        check(L.b200sort_radix_pairs_copy_i32(dk.data_ptr(), dv.data_ptr(), ok.data_ptr(), ov.data_ptr(),
+                                              tk.data_ptr(), tv.data_ptr(), n, ptr, nbytes, stream_ptr()))
+        torch.cuda.synchronize()
+        assert_bit_exact(dk.cpu().numpy(), keys, "pairs copy form: keys modified")
+        assert_bit_exact(dv.cpu().numpy(), vals, "pairs copy form: values modified")
+        return ok[:n].cpu().numpy(), ov[:n].cpu().numpy()
+    check(L.b200sort_radix_pairs_i32(dk.data_ptr(), dv.data_ptr(), tk.data_ptr(), tv.data_ptr(), n, ptr, nbytes,
+                                     stream_ptr()))
+    torch.cuda.synchronize()
+    return dk.cpu().numpy(), dv.cpu().numpy()
+
+
+@pytest.mark.parametrize("dist", ["uniform", "lab_rand100", "and3", "all_equal", "mask_0000ffff", "mask_00ff00ff",
+                                  "skewed90", "descending", "edge_mix"])
+@pytest.mark.parametrize("n", [0, 1, 2, 33, 5119, 5120, 5121, 100003, (1 << 20) + 17])
+def test_sort_by_key_is_stable_and_bit_exact(dist, n):
+    """Sort-by-key: keys AND values equal to the stable oracle's, in place and copy form.
+    Values are the input positions, so the value array is the stable sorting permutation."""
+    if dist == "lab_rand100" and n > 200000:
+        pytest.skip("slow libc loop")
+    keys = datagen.make(dist, n, 37)
+    vals = np.arange(n, dtype=np.int32)
+    want_k, want_v = oracle.sort_pairs(keys, vals)
+    for copy_form in (False, True):
+        got_k, got_v = _gpu_sort_pairs(keys, vals, copy_form)
+        assert_bit_exact(got_k, want_k, f"{dist} n={n} keys copy={copy_form}")
+        assert_bit_exact(got_v, want_v, f"{dist} n={n} values copy={copy_form}")
+
+
+def test_sort_by_key_full_size_2_28():
+    """n = 2^28 pairs: keys sorted, values a permutation that maps back to the input keys, stable."""
+    import torch
+    n = 1 << 28
+    g = torch.Generator(device="cuda"); g.manual_seed(9)
+    keys = torch.randint(-2**15, 2**15, (n,), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)   # many ties
+    orig = keys.clone()
+    vals = torch.arange(n, dtype=torch.int32, device="cuda")
+    tk = torch.empty_like(keys); tv = torch.empty_like(vals)
+    ws, ptr, nbytes = workspace(n, ALGO_RADIX)
+    check(lib().b200sort_radix_pairs_i32(keys.data_ptr(), vals.data_ptr(), tk.data_ptr(), tv.data_ptr(), n, ptr, nbytes,
+                                         stream_ptr()))
+    torch.cuda.synchronize()
+    del tk, tv
+    assert bool((keys[1:] >= keys[:-1]).all().item()), "keys not sorted"
+    assert bool((orig[vals.long()] == keys).all().item()), "values do not point at their keys"
+    ties = keys[1:] == keys[:-1]
+    assert bool((vals[1:][ties] > vals[:-1][ties]).all().item()), "not stable"
+
+
 def test_pass_skipping_on_and_off_agree():
     L = lib()
     try:
