@@ -42,7 +42,8 @@ using OnesweepFn = void (*)(const int32_t *, int32_t *, int32_t *, size_t, int, 
 struct Variant {
     const char *name;
     int mode;
-    int cluster;       // CTAs per cluster (1 = none); 0 marks the persistent pipelined kernel
+    int cluster;       // CTAs per cluster (1 = none); 0 marks the persistent pipelined kernel (2 CTAs per SM),
+                       // -k the same with k CTAs per SM
     int two_level;     // status rows: one per tile plus one per group of kLookGroup tiles
     int threads;
     int tile;
@@ -139,6 +140,10 @@ const Variant kVariants[] = {
     B200_PP2_VARIANT(18),                             // 50: the default until the packed counters (0.728 ms/pass)
     B200_PP2X_VARIANT(22, 0, 1),                      // 51: 11264
     B200_PP2X_VARIANT(24, 0, 1),                      // 52: 12288
+    { "pipelined2_16w_ipt12_kRankAdd_pack1_3ctas", kRankAdd, -3, 1, 512, Pipelined2Shape<12, 1>::kTile,
+      Pipelined2Shape<12, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<12, 0, 0, 1, 3> },   // 53: 3 CTAs per SM, 6144
+    { "pipelined2_16w_ipt10_kRankAdd_pack1_3ctas", kRankAdd, -3, 1, 512, Pipelined2Shape<10, 1>::kTile,
+      Pipelined2Shape<10, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<10, 0, 0, 1, 3> },   // 54: 5120
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
@@ -197,8 +202,8 @@ size_t status_rows(const Variant &var, size_t tiles) {
 int launch_onesweep(const Variant &var, size_t tiles, cudaStream_t s, const int32_t *in, int32_t *out,
                     int32_t *tmp, size_t n, int pass, RadixControl *ctl, uint32_t *cur, uint32_t *next,
                     int follow_plan) {
-    if (var.cluster == 0) {          // persistent: one CTA per resident slot, tiles by ticket
-        const unsigned slots = 2u * kNumSMs;
+    if (var.cluster <= 0) {          // persistent: one CTA per resident slot, tiles by ticket
+        const unsigned slots = (var.cluster == 0 ? 2u : (unsigned)(-var.cluster)) * kNumSMs;
         const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
         var.fn<<<grid, var.threads, var.smem, s>>>(in, out, tmp, n, pass, ctl, cur, next, follow_plan);
         B200_LAUNCH_CHECK();
@@ -389,12 +394,38 @@ int radix_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, vo
 
 // ---- sort-by-key ----------------------------------------------------------------
 // The same four stable passes with a 32-bit value carried beside every key: 16 B/key per pass.
-// One shape only: the packed-counter persistent kernel with 512 x 10 = 5120-key tiles (the values
+// The packed-counter persistent kernel with 512 x 10 = 5120-key tiles (the values
 // take the registers and the shared memory the larger key-only tile uses).  Stable, because every
 // pass is (that is what makes LSD correct in the first place): equal keys keep their input order,
 // the A-before-B rule of SRM/lab.cu:163-170 carried through the whole sort.
-constexpr int kPairsIPT = 10;
-size_t radix_pairs_tile() { return Pipelined2Shape<kPairsIPT, 1, 1>::kTile; }
+// Pairs per thread: 10 (default) or 12 (B200SORT_PAIRS_IPT=12, for A/B).
+template <int IPT>
+int launch_pairs_passes(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const int32_t *v_in, int32_t *v_out,
+                        int32_t *v_tmp, size_t n, RadixControl *ctl, uint32_t *const *status, cudaStream_t s) {
+    static std::atomic<bool> attr_set{false};
+    constexpr size_t smem = Pipelined2Shape<IPT, 1, 1>::kSmemBytes;
+    if (!attr_set.load(std::memory_order_acquire)) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_onesweep_pairs_kernel<IPT>),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set.store(true, std::memory_order_release);
+    }
+    const size_t tiles = div_up(n, (size_t)Pipelined2Shape<IPT, 1, 1>::kTile);
+    const unsigned slots = 2u * kNumSMs;
+    const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
+    for (int pass = 0; pass < kRadixPasses; ++pass) {
+        uint32_t *cur = status[pass & 1];
+        uint32_t *next = (pass + 1 < kRadixPasses) ? status[(pass + 1) & 1] : nullptr;
+        radix_onesweep_pairs_kernel<IPT><<<grid, 512, smem, s>>>(d_in, d_out, d_tmp, n, pass, ctl, cur, next, 1,
+                                                                v_in, v_out, v_tmp);
+        B200_LAUNCH_CHECK();
+    }
+    return B200SORT_OK;
+}
+int pairs_ipt() {
+    static const int v = [] { const char *e = getenv("B200SORT_PAIRS_IPT"); return (e && atoi(e) == 12) ? 12 : 10; }();
+    return v;
+}
+size_t radix_pairs_tile() { return 512u * (size_t)pairs_ipt(); }
 
 int radix_sort_pairs(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const int32_t *v_in, int32_t *v_out,
                      int32_t *v_tmp, size_t n, void *d_ws, size_t ws_bytes, cudaStream_t s) {
@@ -407,13 +438,6 @@ int radix_sort_pairs(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const 
     if ((d_in == d_out) != (v_in == v_out)) return B200SORT_ERR_INVALID;   // the plan is shared by keys and values
     B200_TRY(check_ws(d_ws, ws_bytes, n));
     if (!atomic_order_ok()) return B200SORT_ERR_INVALID;                   // no ballot-ranked pairs shape is compiled
-    static std::atomic<bool> attr_set{false};
-    constexpr size_t smem = Pipelined2Shape<kPairsIPT, 1, 1>::kSmemBytes;
-    if (!attr_set.load(std::memory_order_acquire)) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_onesweep_pairs_kernel<kPairsIPT>),
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set.store(true, std::memory_order_release);
-    }
     B200_TRY(ensure_hist_attr());
     auto *ctl = static_cast<RadixControl *>(d_ws);
     const size_t tiles = div_up(n, radix_pairs_tile());
@@ -428,15 +452,8 @@ int radix_sort_pairs(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const 
     radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_in, n, ctl, status[0], rows * kRadixBins,
                                                                  (uint32_t)skip, in_place);
     B200_LAUNCH_CHECK();
-    const unsigned slots = 2u * kNumSMs;
-    const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
-    for (int pass = 0; pass < kRadixPasses; ++pass) {
-        uint32_t *cur = status[pass & 1];
-        uint32_t *next = (pass + 1 < kRadixPasses) ? status[(pass + 1) & 1] : nullptr;
-        radix_onesweep_pairs_kernel<kPairsIPT><<<grid, 512, smem, s>>>(d_in, d_out, d_tmp, n, pass, ctl, cur, next, 1,
-                                                                      v_in, v_out, v_tmp);
-        B200_LAUNCH_CHECK();
-    }
+    if (pairs_ipt() == 12) B200_TRY(launch_pairs_passes<12>(d_in, d_out, d_tmp, v_in, v_out, v_tmp, n, ctl, status, s));
+    else                   B200_TRY(launch_pairs_passes<10>(d_in, d_out, d_tmp, v_in, v_out, v_tmp, n, ctl, status, s));
     if (skip) {
         const size_t blocks = div_up(div_up(n, 4), 256);
         const unsigned g2 = (unsigned)(blocks < (size_t)kNumSMs * 8 ? blocks : (size_t)kNumSMs * 8);

@@ -741,8 +741,9 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     }
 }
 
-template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0>
-__global__ void __launch_bounds__(512, 2)
+// MINB: CTAs per SM the register allocation is held to (3 with tiles of <= 6144 keys: 40 registers).
+template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0, int MINB = 2>
+__global__ void __launch_bounds__(512, MINB)
 radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                  int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
                                  int follow_plan)
