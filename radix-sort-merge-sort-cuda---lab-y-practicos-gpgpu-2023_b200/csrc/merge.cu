@@ -489,7 +489,9 @@ __device__ __forceinline__ MergeTileGeom32 merge_tile_geom32(const int32_t *in, 
     return g;
 }
 
-__global__ void __launch_bounds__(kSortThreads, 4)
+// MINB: CTAs per SM the register allocation is held to (4: 64 registers, 5: 48, 6: 40).
+template <int MINB>
+__global__ void __launch_bounds__(kSortThreads, MINB)
 merge_pass2_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, size_t n, size_t run,
                    int pair_shift, const uint32_t *__restrict__ splits, size_t t_begin,
                    size_t tiles /* = end of the range */)
@@ -573,20 +575,25 @@ merge_pass2_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, si
 // bit 0: merge pass = k5 (staged output, bounds-tested serial merge) instead of k5'
 // bit 1: block sort tiles of 4096 keys (256 threads) instead of 8192 (512 threads)
 // bit 2: block sort with every round in shared memory (no warp-register bitonic rounds)
+// bits 3-4: k5' with 4 + k CTAs per SM (k = 0, 1, 2)
 static std::atomic<int> g_merge_variant{0};
 int merge_set_variant(int v) {
-    if (v < 0 || v > 7) return B200SORT_ERR_INVALID;
+    if (v < 0 || v >= 24) return B200SORT_ERR_INVALID;
     g_merge_variant.store(v);
     return B200SORT_OK;
 }
-int merge_num_variants() { return 8; }
+int merge_num_variants() { return 24; }
 const char *merge_variant_name(int v) {
-    static const char *names[8] = {
+    static const char *names[24] = {
         "block8192_warpnet_pass2_sentinel_direct_store", "block8192_warpnet_pass1_staged_store",
         "block4096_warpnet_pass2_sentinel_direct_store", "block4096_warpnet_pass1_staged_store",
         "block8192_smemrounds_pass2_sentinel_direct_store", "block8192_smemrounds_pass1_staged_store",
-        "block4096_smemrounds_pass2_sentinel_direct_store", "block4096_smemrounds_pass1_staged_store"};
-    return (v >= 0 && v < 8) ? names[v] : nullptr;
+        "block4096_smemrounds_pass2_sentinel_direct_store", "block4096_smemrounds_pass1_staged_store",
+        "block8192_warpnet_pass2_5ctas", "(8|1)", "block4096_warpnet_pass2_5ctas", "(10|1)",
+        "block8192_smemrounds_pass2_5ctas", "(12|1)", "block4096_smemrounds_pass2_5ctas", "(14|1)",
+        "block8192_warpnet_pass2_6ctas", "(16|1)", "block4096_warpnet_pass2_6ctas", "(18|1)",
+        "block8192_smemrounds_pass2_6ctas", "(20|1)", "block4096_smemrounds_pass2_6ctas", "(22|1)"};
+    return (v >= 0 && v < 24) ? names[v] : nullptr;
 }
 
 size_t merge_block_tile() { return (g_merge_variant.load() & 2) ? kSortTile : 2 * kSortTile; }
@@ -629,13 +636,17 @@ int merge_pass_range(const int32_t *d_in, int32_t *d_out, size_t n, size_t run, 
     if (tile_end > tiles) tile_end = tiles;
     if (tile_begin >= tile_end) return B200SORT_OK;
     const size_t count = tile_end - tile_begin;
-    const size_t slots = (size_t)kNumSMs * 4;              // persistent: 4 CTAs of 256 threads per SM
+    const int variant = g_merge_variant.load();
+    const int per_sm = (variant & 1) ? 4 : 4 + ((variant >> 3) & 3);   // persistent: 4..6 CTAs of 256 threads per SM
+    const size_t slots = (size_t)kNumSMs * per_sm;
     const unsigned grid = (unsigned)(count < slots ? count : slots);
-    if ((g_merge_variant.load() & 1) == 0)
+    if ((variant & 1) == 0)
     {
         int pair_shift = -1;                                   // 2 * run a power of two: shifts instead of divisions
         if ((run & (run - 1)) == 0) { pair_shift = 1; while (((size_t)1 << pair_shift) < 2 * run) ++pair_shift; }
-        merge_pass2_kernel<<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tile_begin, tile_end);
+        if (per_sm == 4)      merge_pass2_kernel<4><<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tile_begin, tile_end);
+        else if (per_sm == 5) merge_pass2_kernel<5><<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tile_begin, tile_end);
+        else                  merge_pass2_kernel<6><<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tile_begin, tile_end);
     }
     else
         merge_pass_kernel<<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, d_splits, tile_begin, tile_end);
