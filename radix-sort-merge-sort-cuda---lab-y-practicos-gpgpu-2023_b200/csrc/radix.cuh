@@ -21,7 +21,8 @@ struct RadixControl {
     uint32_t src_sel[kRadixPasses];            // buffer pass p reads : kSelIn / kSelTmp / kSelOut
     uint32_t dst_sel[kRadixPasses];            // buffer pass p writes: kSelTmp / kSelOut
     uint32_t final_copy;                       // 0 none, else copy from that kSel* buffer to out
-    uint32_t hot[kRadixPasses];                // 1 = some digit value holds > 1/8 of the keys in this pass
+    uint32_t hot[kRadixPasses];                // 0, or 1 + the most frequent digit value of the pass if it
+                                               // holds > 1/8 of the keys
     uint32_t pad1[3];
 };
 constexpr uint32_t kSelIn = 1, kSelTmp = 2, kSelOut = 3;

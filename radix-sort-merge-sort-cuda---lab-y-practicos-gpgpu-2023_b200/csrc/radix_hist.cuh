@@ -137,7 +137,7 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
             for (uint32_t w = 0; w < warp; ++w) add += s_warp_sums[w];
             ctl->base[p][tid] = x - c + add;
             if (skip_enabled && n > 0 && c == (uint32_t)n) s_skip[p] = 1;
-            if ((size_t)c * 8 > n) s_hot[p] = 1;
+            if ((size_t)c * 8 > n) atomicMax(&s_hot[p], ((c >> 6) << 8) | tid);   // the most frequent such digit wins
         }
         __syncthreads();
     }
@@ -152,7 +152,7 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
         uint32_t j = 0, cur = kSelIn;
         for (int p = 0; p < kRadixPasses; ++p) {
             ctl->skip[p] = s_skip[p];
-            ctl->hot[p] = s_hot[p];
+            ctl->hot[p] = s_hot[p] ? 1u + (s_hot[p] & 255u) : 0u;
             ctl->src_sel[p] = cur;
             uint32_t dst = cur;
             if (!s_skip[p]) {

@@ -580,7 +580,10 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
         {
             const uint32_t d0 = digit_of(key[0], shift, flip);
             const uint32_t agree = __ballot_sync(0xffffffffu, d0 == __shfl_sync(0xffffffffu, d0, 0));
-            const bool hot = (follow_plan && ctl->hot[pass] != 0) || __popc(agree) >= 8;
+            // hot digit of the pass (the histogram kernel found one value holding > 1/8 of the keys), else
+            // a locally hot one (a quarter of the warp's first keys agree with lane 0's: sorted input)
+            const uint32_t hot_word = follow_plan ? ctl->hot[pass] : 0u;
+            const bool hot = hot_word != 0 || __popc(agree) >= 8;
             if (!hot) {
 #pragma unroll
                 for (int i = 0; i < IPT; ++i) {
@@ -588,14 +591,18 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
                     rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
                 }
             } else {
+                // the lanes that hold the hot digit are ranked with one ballot and ONE atomic (by their first
+                // lane); the others take the atomic as usual
 #pragma unroll
                 for (int i = 0; i < IPT; ++i) {
                     const uint32_t d = digit_of(key[i], shift, flip);
-                    const bool same = (d == __shfl_sync(0xffffffffu, d, 0));
+                    const uint32_t hd = hot_word ? hot_word - 1u : __shfl_sync(0xffffffffu, d, 0);
+                    const bool same = (d == hd);
                     const uint32_t sm = __ballot_sync(0xffffffffu, same);
+                    const uint32_t leader = (uint32_t)(__ffs(sm) - 1) & 31u;
                     uint32_t r = 0;
-                    if (!same || lane == 0) r = my_half(atomicAdd(wt + d, (lane == 0 ? (uint32_t)__popc(sm) : 1u) << sh));
-                    const uint32_t r0 = __shfl_sync(0xffffffffu, r, 0);
+                    if (!same || lane == leader) r = my_half(atomicAdd(wt + d, (same ? (uint32_t)__popc(sm) : 1u) << sh));
+                    const uint32_t r0 = __shfl_sync(0xffffffffu, r, leader);
                     if (same) r = r0 + __popc(sm & lt);
                     rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
                 }
