@@ -18,8 +18,9 @@
 //                           written (locally or on the peers).
 //
 // The order of keys inside a destination block is irrelevant (a full local sort follows), so the
-// multisplit is unstable; keys are ranked per destination with one ballot and one shared-memory
-// atomicAdd per destination present in the warp.
+// multisplit is unstable and ranks keys with plain shared-memory atomicAdd.  (Measured alternative:
+// peeling the warp's destinations off one at a time -- one ballot and one atomic per destination
+// present -- was slower at 2 GPUs, 1.31 against 1.06 ms: the shuffles cost more than the conflicts.)
 #include "dist.cuh"
 
 #include <cstdlib>
@@ -100,7 +101,7 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
     unsigned long long *s_gbase = reinterpret_cast<unsigned long long *>(s_start + kDistMaxWorld + 2);
     uint8_t *s_owner = reinterpret_cast<uint8_t *>(s_gbase + kDistMaxWorld);  // [2^bits]
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31, lt = lanemask_lt();
+    const uint32_t tid = threadIdx.x;
     const uint32_t nbins = 1u << bits;
     const int shift = 32 - bits;
     for (uint32_t i = tid; i < nbins; i += THREADS) s_owner[i] = (uint8_t)bin_owner[i];
@@ -121,28 +122,13 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
             const uint32_t p = i * THREADS + tid;
             if (p < valid) key[i] = ld_stream(keys + base + p);
         }
-        // Rank inside the tile's destination group.  There are only `world` distinct counters, so a plain
-        // atomicAdd per key serialises 32 / world lanes deep on one address (the kernel was bound by
-        // exactly that at 2 GPUs: 1.06 ms for 0.54 GB over NVLink).  The warp peels its destinations off
-        // one at a time instead: one ballot and ONE atomic per destination present in the warp.
 #pragma unroll
         for (int i = 0; i < kDistIpt; ++i) {
             const uint32_t p = i * THREADS + tid;
-            const bool ok = p < valid;
-            const uint32_t d = ok ? s_owner[key_bits(key[i]) >> shift] : 0xFFu;
-            uint32_t todo = __ballot_sync(0xffffffffu, ok);
-            uint32_t mine = 0;
-            while (todo != 0) {
-                const uint32_t leader = (uint32_t)__ffs(todo) - 1u;
-                const uint32_t dl = __shfl_sync(0xffffffffu, d, leader);
-                const uint32_t m = __ballot_sync(0xffffffffu, d == dl) & todo;
-                uint32_t first = 0;
-                if (lane == leader) first = atomicAdd(&s_cnt[dl], (uint32_t)__popc(m));
-                first = __shfl_sync(0xffffffffu, first, leader);
-                if (ok && d == dl) mine = (dl << 16) | (first + (uint32_t)__popc(m & lt));
-                todo &= ~m;
+            if (p < valid) {
+                const uint32_t d = s_owner[key_bits(key[i]) >> shift];
+                slot[i] = (d << 16) | atomicAdd(&s_cnt[d], 1u);
             }
-            slot[i] = mine;
         }
         __syncthreads();
         if (tid < (uint32_t)world)                     // reserve this tile's share of every destination
