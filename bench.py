@@ -47,6 +47,10 @@ def _ncu_traffic(kernel_substr: str):
             for item in json.load(open(path)):
                 if kernel_substr in item.get("kernel", "") and "dram_bytes_total" in item:
                     best = {"bytes": item["dram_bytes_total"], "source": os.path.relpath(path, ROOT)}
+                    try:     # the pipe that actually bounds these kernels
+                        best["lsu_pct"] = float(item["LSU wavefronts % of peak"].split()[0])
+                    except Exception:
+                        pass
         except Exception:
             pass
     return best
@@ -310,6 +314,11 @@ def ours_single(args) -> None:
                 "whole_sort_gbs": algo_bytes_total / (ms_per_step / 1e3) / 1e9,
                 "whole_sort_frac": algo_bytes_total / (ms_per_step / 1e3) / 1e9 / peaks["hbm_gbs"],
                 "frac_of_nominal_8tbs": achieved / 8000.0, "kernels": kernels}
+    if traffic and "lsu_pct" in traffic:
+        roofline["shared_memory_pipe"] = {
+            "busy_pct": traffic["lsu_pct"], "source": traffic["source"],
+            "note": "l1tex data-pipe wavefronts, % of peak, from the same ncu capture: the kernel's real bound "
+                    "(about 17.5 wavefronts per 32 keys and pass for the onesweep pass, 11 for the merge pass)"}
 
     # ---- end to end through the reference-facing operator, host buffers -------------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
