@@ -162,8 +162,15 @@ int staged_copy(HostArena &a, char *dev, char *host, size_t bytes, bool to_devic
     B200_TRY(a.ensure_stage());
     int dev_id = 0;
     B200_CUDA_TRY(cudaGetDevice(&dev_id));
-    const size_t chunks = div_up(bytes, kStageBytes);
-    const int nthreads = copy_threads();
+    // Small transfers: fewer threads (starting one costs tens of microseconds) and smaller chunks, so
+    // that every thread still has at least two chunks to overlap its memcpy with the DMA engine.
+    int nthreads = copy_threads();
+    const size_t want = bytes / (4u << 20);                    // one thread per 4 MB
+    if ((size_t)nthreads > want) nthreads = want < 1 ? 1 : (int)want;
+    size_t chunk_bytes = align_up(div_up(bytes, (size_t)2 * nthreads), 4096);
+    if (chunk_bytes > kStageBytes) chunk_bytes = kStageBytes;
+    if (chunk_bytes < (256u << 10)) chunk_bytes = 256u << 10;
+    const size_t chunks = div_up(bytes, chunk_bytes);
     int status[kCopyThreads] = {};
     cudaError_t cuda_err[kCopyThreads] = {};
     auto worker = [&](int t) {
@@ -177,8 +184,8 @@ int staged_copy(HostArena &a, char *dev, char *host, size_t bytes, bool to_devic
         int prev_slot = 0;
         for (size_t c = t; c < chunks; c += nthreads, ++k) {
             const int slot = 2 * t + (int)(k & 1);
-            const size_t off = c * kStageBytes;
-            const size_t len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+            const size_t off = c * chunk_bytes;
+            const size_t len = bytes - off < chunk_bytes ? bytes - off : chunk_bytes;
             if (to_device) {
                 if ((e = cudaEventSynchronize(a.ev[slot])) != cudaSuccess) return fail(e);   // chunk free again
                 std::memcpy(a.h_stage[slot], host + off, len);
@@ -188,8 +195,8 @@ int staged_copy(HostArena &a, char *dev, char *host, size_t bytes, bool to_devic
                 if ((e = cudaMemcpyAsync(a.h_stage[slot], dev + off, len, cudaMemcpyDeviceToHost, cs)) != cudaSuccess) return fail(e);
                 if ((e = cudaEventRecord(a.ev[slot], cs)) != cudaSuccess) return fail(e);
                 if (prev_c != (size_t)-1) {       // drain the previous chunk while this one is in flight
-                    const size_t poff = prev_c * kStageBytes;
-                    const size_t plen = bytes - poff < kStageBytes ? bytes - poff : kStageBytes;
+                    const size_t poff = prev_c * chunk_bytes;
+                    const size_t plen = bytes - poff < chunk_bytes ? bytes - poff : chunk_bytes;
                     if ((e = cudaEventSynchronize(a.ev[prev_slot])) != cudaSuccess) return fail(e);
                     std::memcpy(host + poff, a.h_stage[prev_slot], plen);
                 }
@@ -198,8 +205,8 @@ int staged_copy(HostArena &a, char *dev, char *host, size_t bytes, bool to_devic
             }
         }
         if (!to_device && prev_c != (size_t)-1) {
-            const size_t poff = prev_c * kStageBytes;
-            const size_t plen = bytes - poff < kStageBytes ? bytes - poff : kStageBytes;
+            const size_t poff = prev_c * chunk_bytes;
+            const size_t plen = bytes - poff < chunk_bytes ? bytes - poff : chunk_bytes;
             if ((e = cudaEventSynchronize(a.ev[prev_slot])) != cudaSuccess) return fail(e);
             std::memcpy(host + poff, a.h_stage[prev_slot], plen);
         }
