@@ -144,6 +144,11 @@ const Variant kVariants[] = {
       Pipelined2Shape<12, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<12, 0, 0, 1, 3> },   // 53: 3 CTAs per SM, 6144
     { "pipelined2_16w_ipt10_kRankAdd_pack1_3ctas", kRankAdd, -3, 1, 512, Pipelined2Shape<10, 1>::kTile,
       Pipelined2Shape<10, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<10, 0, 0, 1, 3> },   // 54: 5120
+    { "pipelined2_16w_ipt20_kRankAdd_pack1_earlygroup", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
+      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 1> },   // 55: group rows
+                                                      //     made inclusive by their last tile at once
+    { "pipelined2_16w_ipt18_kRankAdd_pack1_earlygroup", kRankAdd, 0, 1, 512, Pipelined2Shape<18, 1>::kTile,
+      Pipelined2Shape<18, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<18, 0, 0, 1, 2, 1> },   // 56
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);

@@ -362,7 +362,10 @@ struct Pipelined2Shape {
         + 128;
 };
 
-template <int IPT, int TIMING, int SPLIT, int PACK, int KV>
+// EG   : the last tile of a group makes its GROUP row inclusive at once (it walks the earlier group rows
+//        right after publishing the group's own total) instead of one iteration later, so that every other
+//        tile's walk over the group rows ends at the first row it reads.
+template <int IPT, int TIMING, int SPLIT, int PACK, int KV, int EG = 0>
 __device__ __forceinline__ void
 radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
@@ -484,6 +487,8 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     uint32_t digit_base = in_b ? ctl->base[pass][bd] : 0u;
     uint32_t p_total = 0, p_in = 0;                           // its count of my digit; in-group prefix if known
     bool p_in_known = false;
+    uint32_t p_g = 0;                                         // EG: its prefix over the earlier groups, if known
+    bool p_g_known = false;
     // !SPLIT: the previous tile's look-back, run by group B alone: fills s_gofs[buf].
     auto resolve_prev = [&](uint32_t pt, int buf) {
         const uint32_t group = pt / kLookGroup, r = pt % kLookGroup;
@@ -497,8 +502,12 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
         }
         uint32_t gprev = 0;
         if (group > 0) {
-            gprev = walk_back<W>(grow - kRadixBins, group);
-            if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + inprev + p_total) & kValueMask));
+            if (EG && p_g_known) {
+                gprev = p_g;                                  // summed (and published) when the tile was published
+            } else {
+                gprev = walk_back<W>(grow - kRadixBins, group);
+                if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + inprev + p_total) & kValueMask));
+            }
         }
         s_gofs[buf * kRadixBins + bd] = digit_base + inprev + gprev - s_tstart[buf * kRadixBins + bd];
     };
@@ -684,12 +693,20 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
             // it has to wait an iteration for the group's total
             p_total = total;
             p_in_known = false;
+            p_g_known = false;
             if (last_of_group) {
                 p_in = (r > 0) ? walk_back<W>(row - kRadixBins, r) : 0u;
                 p_in_known = true;
                 if (r > 0) st_relaxed_gpu(row, kFlagIncl | (p_in + total));
                 uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
                 st_relaxed_gpu(grow, (group == 0 ? kFlagIncl : kFlagLocal) | (p_in + total));
+                if (EG && !SPLIT && group > 0) {
+                    // every row this walk waits for is published by a running CTA before that CTA waits for
+                    // anything (its group's own total first, then its walk), so the walk terminates
+                    p_g = walk_back<W>(grow - kRadixBins, group);
+                    p_g_known = true;
+                    st_relaxed_gpu(grow, kFlagIncl | ((p_g + p_in + total) & kValueMask));
+                }
             }
             __syncwarp();
             B200_STAMP(3);                                    // group B done
@@ -749,13 +766,13 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
 }
 
 // MINB: CTAs per SM the register allocation is held to (3 with tiles of <= 6144 keys: 40 registers).
-template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0, int MINB = 2>
+template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0, int MINB = 2, int EG = 0>
 __global__ void __launch_bounds__(512, MINB)
 radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                  int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
                                  int follow_plan)
 {
-    radix_onesweep_pipelined2_body<IPT, TIMING, SPLIT, PACK, 0>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
+    radix_onesweep_pipelined2_body<IPT, TIMING, SPLIT, PACK, 0, EG>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
                                                                 status_next, follow_plan, nullptr, nullptr, nullptr);
 }
 
