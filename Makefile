@@ -39,6 +39,7 @@ drivers: $(LIB)
 	@mkdir -p build
 	g++ -O2 -std=c++17 -Iinclude -I$(CUDA_INC) tools/b200sort_driver.cpp -o build/b200sort_driver \
 	    -L$(PKG) -lb200sort -Wl,-rpath,'$$ORIGIN/../$(PKG)'
+	g++ -O3 -std=c++17 -fopenmp tools/cpu_baselines.cpp -o build/cpu_baselines
 	@if [ -f "$(SRM)/main.cpp" ]; then \
 	  g++ -O3 -I$(CUDA_INC) "$(SRM)/main.cpp" -o build/sort -L$(PKG) -lb200sort -Wl,-rpath,'$$ORIGIN/../$(PKG)' && \
 	  g++ -O3 -I$(CUDA_INC) "$(SRM)/performanceTest.cpp" -o build/performaceTest -L$(PKG) -lb200sort -Wl,-rpath,'$$ORIGIN/../$(PKG)' && \
