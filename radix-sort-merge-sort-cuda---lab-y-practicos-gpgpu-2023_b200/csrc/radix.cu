@@ -149,6 +149,11 @@ const Variant kVariants[] = {
                                                       //     made inclusive by their last tile at once
     { "pipelined2_16w_ipt18_kRankAdd_pack1_earlygroup", kRankAdd, 0, 1, 512, Pipelined2Shape<18, 1>::kTile,
       Pipelined2Shape<18, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<18, 0, 0, 1, 2, 1> },   // 56
+    { "pipelined2_16w_ipt20_kRankAdd_pack1_overlap", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
+      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 1> },   // 57: no barrier
+                                                      //     between digit phase and staging; B stages under its status loads
+    { "pipelined2_16w_ipt18_kRankAdd_pack1_overlap", kRankAdd, 0, 1, 512, Pipelined2Shape<18, 1>::kTile,
+      Pipelined2Shape<18, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<18, 0, 0, 1, 2, 0, 1> },   // 58
 };
 constexpr int kFallbackVariant = 5;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);

@@ -365,7 +365,10 @@ struct Pipelined2Shape {
 // EG   : the last tile of a group makes its GROUP row inclusive at once (it walks the earlier group rows
 //        right after publishing the group's own total) instead of one iteration later, so that every other
 //        tile's walk over the group rows ends at the first row it reads.
-template <int IPT, int TIMING, int SPLIT, int PACK, int KV, int EG = 0>
+// OVL  : no CTA barrier between the digit phase and the staging.  Group A stages as soon as ITS positions
+//        are final; group B walks the previous tile's tile rows, sends the first window of group-row loads
+//        off, stages while they fly, then finishes the walk.  One CTA barrier before the write-out.
+template <int IPT, int TIMING, int SPLIT, int PACK, int KV, int EG = 0, int OVL = 0>
 __device__ __forceinline__ void
 radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
@@ -377,6 +380,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     constexpr int W = 8;                                      // status rows in flight per thread
     static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in pairs");
     static_assert(kTile + 64 < 65536, "PACK keeps 16-bit positions");
+    static_assert(!(OVL && SPLIT), "OVL restructures the unsplit resolve");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *s_table  = reinterpret_cast<uint32_t *>(smem_raw);                      // [kRows][256]
@@ -520,16 +524,16 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     //           tile's counts, and after SYNC2 combines both prefixes into s_gofs[buf].
     constexpr int W1 = 12, W2 = 8;               // (16, 8) and (8, 8) spill; this pair does not
     uint32_t win2[W2];
-    auto level2_load = [&](uint32_t pt) {
+    auto level2_load = [&](uint32_t pt, uint32_t dg) {
         const uint32_t group = pt / kLookGroup;
-        const uint32_t *first = status_cur + (tiles + group) * kRadixBins + tid - kRadixBins;
+        const uint32_t *first = status_cur + (tiles + group) * kRadixBins + dg - kRadixBins;
 #pragma unroll
         for (int j = 0; j < W2; ++j)
             win2[j] = ((uint32_t)(j + 1) <= group) ? ld_relaxed_gpu(first - (size_t)j * kRadixBins) : kFlagIncl;
     };
-    auto level2_finish = [&](uint32_t pt) {
+    auto level2_finish = [&](uint32_t pt, uint32_t dg) -> uint32_t {
         const uint32_t group = pt / kLookGroup;
-        const uint32_t *first = status_cur + (tiles + group) * kRadixBins + tid - kRadixBins;
+        const uint32_t *first = status_cur + (tiles + group) * kRadixBins + dg - kRadixBins;
         uint32_t acc = 0, back = 1;
         bool have = true;
         for (;;) {
@@ -551,7 +555,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
             if (done) break;
             back += used;
         }
-        s_g2[tid] = acc;
+        return acc;
     };
     auto level1 = [&](uint32_t pt) -> uint32_t {       // group B
         if (p_in_known) return p_in;                 // the last tile of a group summed its group when it published
@@ -625,8 +629,10 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
 
         const bool have_prev = prev_tile != 0xFFFFFFFFu;
         uint32_t q_total_keep = 0, q_in_keep = 0;             // SPLIT, group B: the previous tile's count and in-group prefix
+        uint32_t o_total = 0, o_in = 0, o_g = 0;              // OVL, group B: the same, and its prefix over the groups
+        bool o_g_known = false;
         if (in_a) {
-            if (SPLIT && have_prev && prev_tile / kLookGroup > 0) level2_load(prev_tile);
+            if (SPLIT && have_prev && prev_tile / kLookGroup > 0) level2_load(prev_tile, tid);
             // thread = digit: tile totals -> group B; exclusive scan; warp counts -> positions
             uint32_t total = 0;
 #pragma unroll
@@ -663,7 +669,12 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
                 }
             }
             s_tstart[b * kRadixBins + tid] = tile_start;
-            if (SPLIT && have_prev) { if (prev_tile / kLookGroup > 0) level2_finish(prev_tile); else s_g2[tid] = 0; }
+            if (SPLIT && have_prev) s_g2[tid] = (prev_tile / kLookGroup > 0) ? level2_finish(prev_tile, tid) : 0u;
+            if (OVL) {                                        // positions final: group B may stage; so may group A
+                __threadfence_block();
+                bar_arrive(11, 512);
+                bar_sync(12, kRadixBins);
+            }
             B200_STAMP(3);                                    // group A done
         } else {
             if (SPLIT) {
@@ -684,10 +695,19 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
                 if (last_of_group) status_next[(tiles + group) * kRadixBins + bd] = 0;
             }
             B200_STAMP(10);                                   // published
-            if (!SPLIT) {
+            if (!SPLIT && !OVL) {
                 // ... resolve the PREVIOUS tile's prefix (everything it needs was published long ago) ...
                 if (have_prev) resolve_prev(prev_tile, b ^ 1);
                 B200_STAMP(11);                               // previous tile resolved
+            }
+            if (OVL && have_prev) {
+                // ... the previous tile's in-group prefix now, the first window of its group rows sent off ...
+                o_total = p_total;
+                o_in = level1(prev_tile);
+                o_g_known = EG && p_g_known;
+                o_g = p_g;
+                if (prev_tile / kLookGroup > 0 && !o_g_known) level2_load(prev_tile, bd);
+                B200_STAMP(11);
             }
             // ... and, for the last tile of a group only, sum the group now so that nobody after
             // it has to wait an iteration for the group's total
@@ -709,9 +729,10 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
                 }
             }
             __syncwarp();
+            if (OVL) bar_sync(11, 512);                       // group A's positions are final
             B200_STAMP(3);                                    // group B done
         }
-        __syncthreads();                                      // SYNC2: positions final; previous tile: offsets (SPLIT: both prefixes) known
+        if (!OVL) __syncthreads();                            // SYNC2: positions final; previous tile: offsets (SPLIT: both prefixes) known
         if (SPLIT && in_b && have_prev) combine_prev(prev_tile, b ^ 1, q_total_keep, q_in_keep);
         B200_STAMP(4);
         const uint32_t next = s_misc[8 + ((iter + 1) & 1)];
@@ -739,6 +760,23 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
             __syncthreads();                                  // SYNC3: the previous tile's offsets are in s_gofs
             if (PACK) zero_counters();
         }
+        if (OVL) {
+            if (in_b && have_prev) {                          // finish the previous tile's walk over the group rows
+                const uint32_t pg = prev_tile / kLookGroup;
+                const bool plast = (prev_tile % kLookGroup == kLookGroup - 1) || ((size_t)prev_tile + 1 == tiles);
+                uint32_t gprev = 0;
+                if (pg > 0) {
+                    if (o_g_known) gprev = o_g;
+                    else {
+                        gprev = level2_finish(prev_tile, bd);
+                        if (plast) st_relaxed_gpu(status_cur + (tiles + pg) * kRadixBins + bd,
+                                                  kFlagIncl | ((gprev + o_in + o_total) & kValueMask));
+                    }
+                }
+                s_gofs[(b ^ 1) * kRadixBins + bd] = digit_base + o_in + gprev - s_tstart[(b ^ 1) * kRadixBins + bd];
+            }
+            __syncthreads();                                  // the previous tile's offsets are in s_gofs
+        }
         if (have_prev) write_tile(prev_tile, b ^ 1);
         B200_STAMP(7);                                        // previous tile written
         if (TIMING && g_phase_dbg != nullptr && lane == 0 && (warp == 0 || warp == 8))
@@ -753,7 +791,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
         __syncthreads();
         if (SPLIT) {
             uint32_t q_in = 0;
-            if (in_a) { if (prev_tile / kLookGroup > 0) { level2_load(prev_tile); level2_finish(prev_tile); } else s_g2[tid] = 0; }
+            if (in_a) { if (prev_tile / kLookGroup > 0) { level2_load(prev_tile, tid); s_g2[tid] = level2_finish(prev_tile, tid); } else s_g2[tid] = 0; }
             else q_in = level1(prev_tile);
             __syncthreads();
             if (in_b) combine_prev(prev_tile, b ^ 1, p_total, q_in);
@@ -766,13 +804,13 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
 }
 
 // MINB: CTAs per SM the register allocation is held to (3 with tiles of <= 6144 keys: 40 registers).
-template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0, int MINB = 2, int EG = 0>
+template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0, int MINB = 2, int EG = 0, int OVL = 0>
 __global__ void __launch_bounds__(512, MINB)
 radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                  int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
                                  int follow_plan)
 {
-    radix_onesweep_pipelined2_body<IPT, TIMING, SPLIT, PACK, 0, EG>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
+    radix_onesweep_pipelined2_body<IPT, TIMING, SPLIT, PACK, 0, EG, OVL>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
                                                                 status_next, follow_plan, nullptr, nullptr, nullptr);
 }
 
