@@ -25,6 +25,7 @@
 #include "radix_tile.cuh"
 #include "radix_pipelined.cuh"
 #include "radix_misc.cuh"
+#include "radix_small.cuh"
 
 #include <atomic>
 #include <cstdlib>
@@ -182,6 +183,9 @@ int atomic_order_ok() {
 // failed (or was told to skip) the self-test.
 int effective_variant();
 std::atomic<int> g_skip_enabled{1};
+std::atomic<int> g_small_enabled{1};      // one-CTA sort for n <= 8192 (B200SORT_RADIX_SMALL=0 or any explicit
+                                          // b200sort_radix_set_variant call switches it off: sweeps and the
+                                          // all-shapes test must reach the shape they selected)
 std::atomic<bool> g_attrs_set[kNumVariants];
 
 int ensure_smem_attr(int v) {
@@ -267,6 +271,8 @@ const char *radix_variant_name(int v) { return (v >= 0 && v < kNumVariants) ? kV
 int radix_set_variant(int v) {
     if (v < 0 || v >= kNumVariants) return B200SORT_ERR_INVALID;
     g_variant.store(v);
+    const char *e = getenv("B200SORT_RADIX_SMALL");
+    g_small_enabled.store((v == 0 && !(e && e[0] == '0')) ? 1 : 0);   // 0 = the default configuration
     return B200SORT_OK;
 }
 void radix_set_skip(int enabled) { g_skip_enabled.store(enabled ? 1 : 0); }
@@ -357,6 +363,19 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
         return B200SORT_OK;
     }
     B200_TRY(check_ws(d_ws, ws_bytes, n));
+    // k0: up to 8192 keys are sorted by one CTA in one launch (untimed calls only: the timed form reports
+    // the pipeline's kernels).  Same lane-ordered atomic rank as the pass kernel, same gate.
+    if (ms == nullptr && n <= (size_t)kSmallTile && g_small_enabled.load() && atomic_order_ok()) {
+        static std::atomic<bool> small_attr{false};
+        if (!small_attr.load(std::memory_order_acquire)) {
+            B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_small_kernel),
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemBytes));
+            small_attr.store(true, std::memory_order_release);
+        }
+        radix_small_kernel<<<1, kSmallThreads, kSmallSmemBytes, s>>>(d_in, d_out, (uint32_t)n);
+        B200_LAUNCH_CHECK();
+        return B200SORT_OK;
+    }
     const int v = effective_variant();
     B200_TRY(ensure_smem_attr(v));
     B200_TRY(ensure_hist_attr());
