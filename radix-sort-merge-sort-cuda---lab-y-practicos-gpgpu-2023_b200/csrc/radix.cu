@@ -15,6 +15,7 @@
 //              atomicOr table / atomicAdd; one- or two-level look-back; optional clusters;
 //        radix_onesweep_pipelined_kernel (radix_pipelined.cuh)  14 worker warps + 2 chain warps.
 //   k3  radix_final_copy_kernel, radix_atomic_order_selftest_kernel (radix_misc.cuh)
+//   k0  radix_small_kernel (radix_small.cuh)  n <= 8192: all four passes in one CTA, one launch
 // This file is the host side: the shape table, workspace layout, launches.
 //
 // Signed order: digits are taken from key ^ 0x80000000 (only the top digit changes).
