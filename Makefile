@@ -12,6 +12,10 @@ CSRC    := $(PKG)/csrc
 NVCC    ?= nvcc
 ARCH    := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Wno-deprecated-gpu-targets
+# make EXPERIMENTS=1: also compile every onesweep / merge shape that was measured and lost (sweeps only)
+ifeq ($(EXPERIMENTS),1)
+NVFLAGS += -DB200SORT_EXPERIMENTS
+endif
 REFROOT ?= /root/reference
 SRM     := $(REFROOT)/Sord Radix y Merge
 

@@ -217,6 +217,101 @@ def _check_sorted(torch, out, src) -> None:
         "bench: output is not a permutation of the input (sum differs)"
 
 
+
+def _measure_config(L, torch, dev, algo_name: str, dist: str, log2n: int, steps: int, peaks: dict, bufs: dict) -> dict:
+    """One row of the `configs` block: `steps` timed sorts (after 3 warm-up sorts) of 2^log2n `dist` keys
+    with `algo_name`, the per-kernel CUDA-event times of one more sort, and the checks the bench can afford
+    at this size (sortedness + multiset sum)."""
+    import ctypes
+
+    from b200sort._lib import ALGO_MERGE, ALGO_RADIX, check
+    algo = {"radix": ALGO_RADIX, "merge": ALGO_MERGE}[algo_name]
+    n = 1 << log2n
+    key = (dist, log2n)
+    if bufs.get("key") != key:                      # the same keys serve radix and merge
+        bufs["src"] = None
+        bufs["src"] = _make_device_keys(torch, n, dist, 1, dev)
+        bufs["key"] = key
+    if bufs.get("n") != n:
+        bufs["out"] = bufs["tmp"] = None
+        bufs["out"] = torch.empty(n, dtype=torch.int32, device=dev)
+        bufs["tmp"] = torch.empty(n, dtype=torch.int32, device=dev)
+        bufs["n"] = n
+    src, out, tmp = bufs["src"], bufs["out"], bufs["tmp"]
+    ws_bytes = L.b200sort_workspace_bytes(n, algo)
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+    ws_ptr = ws.data_ptr() + (-ws.data_ptr()) % 256
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        check(L.b200sort_sort_copy_i32(algo, src.data_ptr(), out.data_ptr(), tmp.data_ptr(), n, ws_ptr, ws_bytes, stream))
+    for _ in range(3):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    _check_sorted(torch, out, src)
+    kms = (ctypes.c_float * 8)()
+    check(L.b200sort_sort_timed_i32(algo, src.data_ptr(), out.data_ptr(), tmp.data_ptr(), n, ws_ptr, ws_bytes, stream,
+                                    ctypes.cast(kms, ctypes.c_void_p)))
+    row = {"algo": algo_name, "dist": dist, "log2n": log2n, "steps": steps, "ms_per_step": ms,
+           "keys_per_s": n / (ms / 1e3), "checked": "sorted + multiset sum",
+           "l2": "input larger than L2" if 4 * n > 126e6 else "input fits L2 (64 MiB of 126 MB): flushed by the "
+                 "sort's own 2x64 MiB ping-pong traffic only; HBM fractions are quoted all the same"}
+    if algo == ALGO_RADIX:
+        pass_ms = [kms[i] for i in range(1, 5)]
+        ran = [p for p in pass_ms if p > 0.25 * max(pass_ms)] or pass_ms
+        executed = len(ran) if n >= (1 << 22) else 4
+        k_ms = sum(ran) / len(ran)
+        row.update({"histogram_ms": kms[0], "pass_ms": pass_ms, "passes_executed": executed,
+                    "pass_frac": 8.0 * n / (k_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                    "whole_sort_frac": (4.0 + 8.0 * executed) * n / (ms / 1e3) / 1e9 / peaks["hbm_gbs"]})
+    else:
+        passes = int(round(kms[2]))
+        row.update({"block_sort_ms": kms[0], "merge_passes_ms": kms[1], "merge_passes": passes,
+                    "pass_frac": 8.0 * n / (kms[1] / max(passes, 1) / 1e3) / 1e9 / peaks["hbm_gbs"],
+                    "block_sort_frac": 8.0 * n / (kms[0] / 1e3) / 1e9 / peaks["hbm_gbs"] if kms[0] > 0 else None,
+                    "whole_sort_frac": 8.0 * (1 + passes) * n / (ms / 1e3) / 1e9 / peaks["hbm_gbs"]})
+    return row
+
+
+# BASELINE.json configs 2-5 on one GPU: every row is measured in the default run (config 1 is the parity
+# suite's size; the headline line itself is config 2/3's radix sort at the metric's n)
+CONFIG_ROWS = (
+    ("config3: merge sort, 2^28 uniform", "merge", "uniform", 28),
+    ("config4: radix, 2^28 skewed90", "radix", "skewed90", 28),
+    ("config4: merge, 2^28 skewed90", "merge", "skewed90", 28),
+    ("config4: radix, 2^28 ascending (already sorted)", "radix", "ascending", 28),
+    ("config4: merge, 2^28 ascending (already sorted)", "merge", "ascending", 28),
+    ("config4: radix, 2^28 descending (reverse sorted)", "radix", "descending", 28),
+    ("config4: merge, 2^28 descending (reverse sorted)", "merge", "descending", 28),
+    ("config2: radix, 2^24 uniform", "radix", "uniform", 24),
+    ("config2: radix, 2^24 and3 (AND of 3 uniform words)", "radix", "and3", 24),
+    ("config2: radix, 2^24 mask_0000ffff", "radix", "mask_0000ffff", 24),
+    ("config2: radix, 2^24 mask_00ff00ff", "radix", "mask_00ff00ff", 24),
+    ("config5 denominator: radix, 2^30 uniform on ONE GPU", "radix", "uniform", 30),
+)
+
+
+def _configs_block(L, torch, dev, peaks: dict, steps: int) -> list:
+    rows, bufs = [], {}
+    for name, algo_name, dist, log2n in CONFIG_ROWS:
+        try:
+            row = _measure_config(L, torch, dev, algo_name, dist, log2n, steps, peaks, bufs)
+        except Exception as e:                      # a row that cannot run says so instead of vanishing
+            row = {"algo": algo_name, "dist": dist, "log2n": log2n, "error": repr(e)[:200]}
+        row["config"] = name
+        rows.append(row)
+    bufs.clear()
+    torch.cuda.empty_cache()
+    return rows
+
+
 def ours_single(args) -> None:
     import ctypes
 
@@ -368,6 +463,10 @@ def ours_single(args) -> None:
                "sample": f"one sort of 2^{log2m} {args.dist} keys (seed 1), {dt:.2f} s; {what}",
                "host_cores_available": os.cpu_count()}
 
+    del src, out, tmp, ws
+    torch.cuda.empty_cache()
+    configs = None if args.no_configs else _configs_block(L, torch, dev, peaks, args.config_steps)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -381,7 +480,7 @@ def ours_single(args) -> None:
                    "atomic_order_selftest": bool(L.b200sort_radix_atomic_order_ok()),
                    "radix_tile": int(L.b200sort_radix_tile())},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-        "clocks": sampler.summary(t0, t1),
+        "clocks": sampler.summary(t0, t1), "configs": configs,
     }
     print(json.dumps(line), flush=True)
 
@@ -400,6 +499,8 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-log2n", type=int, default=27, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 2-5 rows")
+    ap.add_argument("--config-steps", type=int, default=4, help="timed sorts per row of the configs block")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU exchange: fused peer-write scatter (default) or NCCL all-to-all")
     args = ap.parse_args()

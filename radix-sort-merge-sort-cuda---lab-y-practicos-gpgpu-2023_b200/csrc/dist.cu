@@ -259,16 +259,13 @@ int dist_partition(const int32_t *d_keys, size_t n, int bits, int world, int32_t
     // Two compiled shapes: 512 threads x 2 CTAs/SM (8192-key tiles) and 256 threads x 4 CTAs/SM
     // (4096-key tiles, more tiles in flight per SM).  B200SORT_DIST_SHAPE=1 selects the second.
     static const int shape = [] { const char *e = getenv("B200SORT_DIST_SHAPE"); return (e && e[0] == '1') ? 1 : 0; }();
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel<512, 2>),
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)partition_smem(B200SORT_DIST_BITS_MAX, 512)));
-        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel<256, 4>),
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)partition_smem(B200SORT_DIST_BITS_MAX, 256)));
-        attr_set = true;
-    }
+    // function attributes are per device: set before every launch
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel<512, 2>),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)partition_smem(B200SORT_DIST_BITS_MAX, 512)));
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel<256, 4>),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)partition_smem(B200SORT_DIST_BITS_MAX, 256)));
     auto *cursor = static_cast<unsigned long long *>(d_ws);
     B200_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long) * kDistMaxWorld, s));
     if (shape == 0) {

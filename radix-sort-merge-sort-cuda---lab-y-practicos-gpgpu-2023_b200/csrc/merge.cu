@@ -576,13 +576,20 @@ merge_pass2_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, si
 // bit 1: block sort tiles of 4096 keys (256 threads) instead of 8192 (512 threads)
 // bit 2: block sort with every round in shared memory (no warp-register bitonic rounds)
 // bits 3-4: k5' with 4 + k CTAs per SM (k = 0, 1, 2)
+// The shipped library compiles variants 0 (default) and 1 (the staged-store pass, kept for A/B); the other 22
+// were measured in round 1 (profiles/r01_merge_variants.txt) and need make EXPERIMENTS=1.
+#ifdef B200SORT_EXPERIMENTS
+constexpr int kMergeVariants = 24;
+#else
+constexpr int kMergeVariants = 2;
+#endif
 static std::atomic<int> g_merge_variant{0};
 int merge_set_variant(int v) {
-    if (v < 0 || v >= 24) return B200SORT_ERR_INVALID;
+    if (v < 0 || v >= kMergeVariants) return B200SORT_ERR_INVALID;
     g_merge_variant.store(v);
     return B200SORT_OK;
 }
-int merge_num_variants() { return 24; }
+int merge_num_variants() { return kMergeVariants; }
 const char *merge_variant_name(int v) {
     static const char *names[24] = {
         "block8192_warpnet_pass2_sentinel_direct_store", "block8192_warpnet_pass1_staged_store",
@@ -610,10 +617,14 @@ int merge_block_sort(const int32_t *d_in, int32_t *d_out, size_t n, cudaStream_t
     else {
         const bool small = merge_block_tile() == (size_t)kSortTile, net = (g_merge_variant.load() & 4) == 0;
         const unsigned g1 = (unsigned)div_up(n, kSortTile), g2 = (unsigned)div_up(n, 2 * kSortTile);
+#ifdef B200SORT_EXPERIMENTS
         if (small && net)       block_sort_kernel<kSortThreads, 1><<<g1, kSortThreads, 0, s>>>(d_in, d_out, n);
         else if (small)         block_sort_kernel<kSortThreads, 0><<<g1, kSortThreads, 0, s>>>(d_in, d_out, n);
-        else if (net)           block_sort_kernel<2 * kSortThreads, 1><<<g2, 2 * kSortThreads, 0, s>>>(d_in, d_out, n);
-        else                    block_sort_kernel<2 * kSortThreads, 0><<<g2, 2 * kSortThreads, 0, s>>>(d_in, d_out, n);
+        else if (!net)          block_sort_kernel<2 * kSortThreads, 0><<<g2, 2 * kSortThreads, 0, s>>>(d_in, d_out, n);
+        else
+#endif
+        { (void)small; (void)net; (void)g1;
+          block_sort_kernel<2 * kSortThreads, 1><<<g2, 2 * kSortThreads, 0, s>>>(d_in, d_out, n); }
     }
     B200_LAUNCH_CHECK();
     return B200SORT_OK;
@@ -644,9 +655,12 @@ int merge_pass_range(const int32_t *d_in, int32_t *d_out, size_t n, size_t run, 
     {
         int pair_shift = -1;                                   // 2 * run a power of two: shifts instead of divisions
         if ((run & (run - 1)) == 0) { pair_shift = 1; while (((size_t)1 << pair_shift) < 2 * run) ++pair_shift; }
-        if (per_sm == 4)      merge_pass2_kernel<4><<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tile_begin, tile_end);
-        else if (per_sm == 5) merge_pass2_kernel<5><<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tile_begin, tile_end);
-        else                  merge_pass2_kernel<6><<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tile_begin, tile_end);
+#ifdef B200SORT_EXPERIMENTS
+        if (per_sm == 5)      merge_pass2_kernel<5><<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tile_begin, tile_end);
+        else if (per_sm == 6) merge_pass2_kernel<6><<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tile_begin, tile_end);
+        else
+#endif
+        merge_pass2_kernel<4><<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, pair_shift, d_splits, tile_begin, tile_end);
     }
     else
         merge_pass_kernel<<<grid, kSortThreads, 0, s>>>(d_in, d_out, n, run, d_splits, tile_begin, tile_end);
@@ -676,7 +690,11 @@ int merge_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, vo
     // buffer makes that so.  d_in is only ever read by the block sort.
     int32_t *src = (passes % 2 == 0) ? d_out : d_tmp;
     int32_t *dst = (passes % 2 == 0) ? d_tmp : d_out;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    struct Events {
+        cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+        ~Events() { for (auto &x : e) if (x) cudaEventDestroy(x); }
+    } events;
+    cudaEvent_t (&ev)[3] = events.e;
     if (ms) {
         for (auto &e : ev) B200_CUDA_TRY(cudaEventCreate(&e));
         B200_CUDA_TRY(cudaEventRecord(ev[0], s));
@@ -694,7 +712,6 @@ int merge_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, vo
         B200_CUDA_TRY(cudaEventElapsedTime(&ms[0], ev[0], ev[1]));   // block sort
         B200_CUDA_TRY(cudaEventElapsedTime(&ms[1], ev[1], ev[2]));   // all merge passes
         ms[2] = (float)passes;
-        for (auto &e : ev) cudaEventDestroy(e);
     }
     return B200SORT_OK;
 }

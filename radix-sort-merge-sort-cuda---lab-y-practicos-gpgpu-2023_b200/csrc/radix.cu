@@ -25,11 +25,13 @@
 #include "radix_hist.cuh"
 #include "radix_tile.cuh"
 #include "radix_pipelined.cuh"
+#include "radix_tma.cuh"
 #include "radix_misc.cuh"
 #include "radix_small.cuh"
 
 #include <atomic>
 #include <cstdlib>
+#include <mutex>
 
 namespace b200sort {
 
@@ -86,6 +88,17 @@ struct Variant {
       Pipelined2Shape<I, P>::kSmemBytes, radix_onesweep_pipelined2_kernel<I, 0, S, P> }
 
 const Variant kVariants[] = {
+    // ---- the shipped shapes ------------------------------------------------------------------------------------
+    B200_PP2X_VARIANT(20, 0, 1),               //  0: DEFAULT: persistent CTAs, 10240-key tiles, delayed two-level look-back,
+                                               //     16-bit counters (two warps per row), write-out by the load/store pipe
+    { "tma_16w_ipt20_kRankAdd_tmem_parked_bulk_store", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes,
+      radix_onesweep_tma_kernel<0> },          //  1: keys parked in tensor memory, late co-aligned staging, TMA write-out
+    B200_VARIANT(16, 16, 2, kRankBallot, 1),   //  2: the documented-behaviour fallback (ballot-ranked, one tile per CTA)
+    { "TIMING_tma_16w_ipt20", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes, radix_onesweep_tma_kernel<1> },   //  3
+    { "TIMING_pipelined2_ipt20_pack", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
+      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 1, 0, 1> },   //  4
+#ifdef B200SORT_EXPERIMENTS
+    // ---- every other shape measured in rounds 1-2 (profiles/r01_onesweep_variants.md): make EXPERIMENTS=1 ----------
     B200_PP2X_VARIANT(20, 0, 1),               //  0: DEFAULT (fastest measured, 0.712 ms/pass): persistent CTAs,
                                                //     10240-key tiles, delayed two-level look-back, 16-bit counters
                                                //     (two warps per row)
@@ -156,27 +169,47 @@ const Variant kVariants[] = {
                                                       //     between digit phase and staging; B stages under its status loads
     { "pipelined2_16w_ipt18_kRankAdd_pack1_overlap", kRankAdd, 0, 1, 512, Pipelined2Shape<18, 1>::kTile,
       Pipelined2Shape<18, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<18, 0, 0, 1, 2, 0, 1> },   // 58
+#endif
 };
-constexpr int kFallbackVariant = 5;
+constexpr int kFallbackVariant = 2;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 std::atomic<int> g_variant{0};
-std::atomic<int> g_atomic_order{-1};      // -1 unknown, 0 the self-test failed, 1 it passed
+// Verdict of the lane-order self-test PER DEVICE: -1 unknown, 0 failed (or B200SORT_RANK_SAFE=1), 1 passed.
+constexpr int kMaxDevices = 64;
+std::atomic<int> g_atomic_order[kMaxDevices];
+std::mutex g_selftest_mu;
+struct AtomicOrderInit { AtomicOrderInit() { for (auto &a : g_atomic_order) a.store(-1); } } g_atomic_order_init;
 
+// Runs the self-test on the current device unless its verdict is cached.  Called from b200sort_device_check()
+// (the explicit init) and, as a fallback, lazily from the first sort on a device: it allocates, launches on
+// a private stream and BLOCKS, so callers that capture CUDA graphs must call b200sort_device_check() first.
 int atomic_order_ok() {
-    int v = g_atomic_order.load(std::memory_order_acquire);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); return 0; }
+    int v = g_atomic_order[dev].load(std::memory_order_acquire);
+    if (v >= 0) return v;
+    std::lock_guard<std::mutex> lock(g_selftest_mu);
+    v = g_atomic_order[dev].load(std::memory_order_acquire);
     if (v >= 0) return v;
     const char *env = getenv("B200SORT_RANK_SAFE");
-    if (env != nullptr && env[0] == '1') { g_atomic_order.store(0); return 0; }
+    if (env != nullptr && env[0] == '1') { g_atomic_order[dev].store(0); return 0; }
     uint32_t *d_bad = nullptr, h_bad = 1;
-    if (cudaMalloc(&d_bad, sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); return 0; }
-    cudaMemset(d_bad, 0, sizeof(uint32_t));
-    radix_atomic_order_selftest_kernel<<<kNumSMs * 2, 512>>>(d_bad);
-    ++g_launch_count;
-    if (cudaMemcpy(&h_bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); h_bad = 1; }
-    cudaFree(d_bad);
+    cudaStream_t st = nullptr;
+    bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&d_bad, sizeof(uint32_t)) == cudaSuccess &&
+              cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), st) == cudaSuccess;
+    if (ok) {
+        radix_atomic_order_selftest_kernel<<<kNumSMs * 2, 512, 0, st>>>(d_bad);
+        ++g_launch_count;
+        ok = cudaMemcpyAsync(&h_bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+             cudaStreamSynchronize(st) == cudaSuccess;
+    }
+    if (!ok) { cudaGetLastError(); h_bad = 1; }
+    if (d_bad) cudaFree(d_bad);
+    if (st) cudaStreamDestroy(st);
     v = (h_bad == 0) ? 1 : 0;
-    g_atomic_order.store(v, std::memory_order_release);
+    g_atomic_order[dev].store(v, std::memory_order_release);
     return v;
 }
 
@@ -184,28 +217,21 @@ int atomic_order_ok() {
 // failed (or was told to skip) the self-test.
 int effective_variant();
 std::atomic<int> g_skip_enabled{1};
-std::atomic<int> g_small_enabled{1};      // one-CTA sort for n <= 8192 (B200SORT_RADIX_SMALL=0 or any explicit
-                                          // b200sort_radix_set_variant call switches it off: sweeps and the
-                                          // all-shapes test must reach the shape they selected)
-std::atomic<bool> g_attrs_set[kNumVariants];
-
+// one-CTA sort for n <= 8192: B200SORT_RADIX_SMALL=0 in the environment or any explicit
+// b200sort_radix_set_variant call other than 0 switches it off (sweeps and the all-shapes test must reach
+// the shape they selected)
+const bool g_small_env_on = [] { const char *e = getenv("B200SORT_RADIX_SMALL"); return !(e && e[0] == '0'); }();
+std::atomic<int> g_small_enabled{g_small_env_on ? 1 : 0};
+// Function attributes are per device, so they are set before every launch instead of once per process
+// (the call costs well under a microsecond).
 int ensure_smem_attr(int v) {
-    if (!g_attrs_set[v].load(std::memory_order_acquire)) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(kVariants[v].fn),
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)kVariants[v].smem));
-        g_attrs_set[v].store(true, std::memory_order_release);
-    }
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(kVariants[v].fn),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVariants[v].smem));
     return B200SORT_OK;
 }
-
-std::atomic<bool> g_hist_attr_set{false};
 int ensure_hist_attr() {
-    if (!g_hist_attr_set.load(std::memory_order_acquire)) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_histogram_kernel),
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHistSmemBytes));
-        g_hist_attr_set.store(true, std::memory_order_release);
-    }
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_histogram_kernel),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHistSmemBytes));
     return B200SORT_OK;
 }
 
@@ -272,8 +298,7 @@ const char *radix_variant_name(int v) { return (v >= 0 && v < kNumVariants) ? kV
 int radix_set_variant(int v) {
     if (v < 0 || v >= kNumVariants) return B200SORT_ERR_INVALID;
     g_variant.store(v);
-    const char *e = getenv("B200SORT_RADIX_SMALL");
-    g_small_enabled.store((v == 0 && !(e && e[0] == '0')) ? 1 : 0);   // 0 = the default configuration
+    g_small_enabled.store((v == 0 && g_small_env_on) ? 1 : 0);        // 0 = the default configuration
     return B200SORT_OK;
 }
 void radix_set_skip(int enabled) { g_skip_enabled.store(enabled ? 1 : 0); }
@@ -290,17 +315,20 @@ int radix_histogram(const int32_t *d_keys, size_t n, uint32_t *d_hist, cudaStrea
     // Standalone histogram (unit tests, per-kernel timing): d_hist doubles as the control block's
     // histogram area, so a scratch control block is not needed -- the kernel is given a control
     // block that lives in a small static device allocation.
-    static thread_local RadixControl *scratch = nullptr;
-    if (scratch == nullptr) B200_CUDA_TRY(cudaMalloc(&scratch, kRadixControlBytes));
-    B200_TRY(ensure_hist_attr());
-    B200_CUDA_TRY(cudaMemsetAsync(scratch, 0, kRadixZeroBytes, s));
-    if (n > 0) {
+    RadixControl *scratch = nullptr;
+    B200_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch), kRadixControlBytes, s));
+    int rc = ensure_hist_attr();
+    if (rc == B200SORT_OK) rc = record_cuda(cudaMemsetAsync(scratch, 0, kRadixZeroBytes, s));
+    if (rc == B200SORT_OK && n > 0) {
         radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_keys, n, scratch, nullptr, 0, 0, 0);
-        B200_LAUNCH_CHECK();
+        ++g_launch_count;
+        rc = record_cuda(cudaGetLastError());
     }
-    B200_CUDA_TRY(cudaMemcpyAsync(d_hist, scratch->hist, sizeof(uint32_t) * kRadixPasses * kRadixBins,
-                                  cudaMemcpyDeviceToDevice, s));
-    return B200SORT_OK;
+    if (rc == B200SORT_OK)
+        rc = record_cuda(cudaMemcpyAsync(d_hist, scratch->hist, sizeof(uint32_t) * kRadixPasses * kRadixBins,
+                                         cudaMemcpyDeviceToDevice, s));
+    cudaFreeAsync(scratch, s);
+    return rc;
 }
 
 static int check_ws(void *d_ws, size_t ws_bytes, size_t n) {
@@ -334,8 +362,9 @@ namespace {
 struct StepTimer {
     cudaStream_t s;
     float *ms;
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[8] = {};
     int n = 0;
+    ~StepTimer() { for (auto &e : ev) if (e) cudaEventDestroy(e); }
     int begin() {
         if (!ms) return B200SORT_OK;
         for (auto &e : ev) B200_CUDA_TRY(cudaEventCreate(&e));
@@ -350,7 +379,6 @@ struct StepTimer {
         if (!ms) return B200SORT_OK;
         B200_CUDA_TRY(cudaEventSynchronize(ev[n - 1]));
         for (int i = 0; i + 1 < n; ++i) B200_CUDA_TRY(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
-        for (auto &e : ev) cudaEventDestroy(e);
         return B200SORT_OK;
     }
 };
@@ -367,12 +395,8 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
     // k0: up to 8192 keys are sorted by one CTA in one launch (untimed calls only: the timed form reports
     // the pipeline's kernels).  Same lane-ordered atomic rank as the pass kernel, same gate.
     if (ms == nullptr && n <= (size_t)kSmallTile && g_small_enabled.load() && atomic_order_ok()) {
-        static std::atomic<bool> small_attr{false};
-        if (!small_attr.load(std::memory_order_acquire)) {
-            B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_small_kernel),
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemBytes));
-            small_attr.store(true, std::memory_order_release);
-        }
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_small_kernel),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemBytes));
         radix_small_kernel<<<1, kSmallThreads, kSmallSmemBytes, s>>>(d_in, d_out, (uint32_t)n);
         B200_LAUNCH_CHECK();
         return B200SORT_OK;
@@ -432,13 +456,9 @@ int radix_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, vo
 template <int IPT>
 int launch_pairs_passes(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const int32_t *v_in, int32_t *v_out,
                         int32_t *v_tmp, size_t n, RadixControl *ctl, uint32_t *const *status, cudaStream_t s) {
-    static std::atomic<bool> attr_set{false};
     constexpr size_t smem = Pipelined2Shape<IPT, 1, 1>::kSmemBytes;
-    if (!attr_set.load(std::memory_order_acquire)) {
-        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_onesweep_pairs_kernel<IPT>),
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set.store(true, std::memory_order_release);
-    }
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_onesweep_pairs_kernel<IPT>),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t tiles = div_up(n, (size_t)Pipelined2Shape<IPT, 1, 1>::kTile);
     const unsigned slots = 2u * kNumSMs;
     const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
