@@ -97,6 +97,9 @@ const Variant kVariants[] = {
     { "TIMING_tma_16w_ipt20", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes, radix_onesweep_tma_kernel<1> },   //  3
     { "TIMING_pipelined2_ipt20_pack", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
       Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 1, 0, 1> },   //  4
+    { "pipelined2_16w_ipt20_kRankAdd_pack1_late_ticket", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
+      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1> },   //  5: variant 0 with the
+                                               //     ticket drawn after the look-back
 #ifdef B200SORT_EXPERIMENTS
     // ---- every other shape measured in rounds 1-2 (profiles/r01_onesweep_variants.md): make EXPERIMENTS=1 ----------
     B200_PP2X_VARIANT(20, 0, 1),               //  0: DEFAULT (fastest measured, 0.712 ms/pass): persistent CTAs,

@@ -368,7 +368,7 @@ struct Pipelined2Shape {
 // OVL  : no CTA barrier between the digit phase and the staging.  Group A stages as soon as ITS positions
 //        are final; group B walks the previous tile's tile rows, sends the first window of group-row loads
 //        off, stages while they fly, then finishes the walk.  One CTA barrier before the write-out.
-template <int IPT, int TIMING, int SPLIT, int PACK, int KV, int EG = 0, int OVL = 0>
+template <int IPT, int TIMING, int SPLIT, int PACK, int KV, int EG = 0, int OVL = 0, int LATE = 0>
 __device__ __forceinline__ void
 radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
@@ -625,7 +625,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
         B200_STAMP(1);                                        // ranked
         __syncthreads();                                      // SYNC1: counts are final
         B200_STAMP(2);
-        if (tid == 0) s_misc[8 + ((iter + 1) & 1)] = atomicAdd(&ctl->ticket[pass], 1u);
+        if (!LATE && tid == 0) s_misc[8 + ((iter + 1) & 1)] = atomicAdd(&ctl->ticket[pass], 1u);
 
         const bool have_prev = prev_tile != 0xFFFFFFFFu;
         uint32_t q_total_keep = 0, q_in_keep = 0;             // SPLIT, group B: the previous tile's count and in-group prefix
@@ -729,6 +729,9 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
                 }
             }
             __syncwarp();
+            // LATE: the next tile's ticket is drawn AFTER the look-back (the one phase whose length varies), so that
+            // from ticket to publication every tile takes the same time and tiles are published in ticket order
+            if (LATE && tid == kRadixBins) s_misc[8 + ((iter + 1) & 1)] = atomicAdd(&ctl->ticket[pass], 1u);
             if (OVL) bar_sync(11, 512);                       // group A's positions are final
             B200_STAMP(3);                                    // group B done
         }
@@ -804,13 +807,13 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
 }
 
 // MINB: CTAs per SM the register allocation is held to (3 with tiles of <= 6144 keys: 40 registers).
-template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0, int MINB = 2, int EG = 0, int OVL = 0>
+template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0, int MINB = 2, int EG = 0, int OVL = 0, int LATE = 0>
 __global__ void __launch_bounds__(512, MINB)
 radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                  int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
                                  int follow_plan)
 {
-    radix_onesweep_pipelined2_body<IPT, TIMING, SPLIT, PACK, 0, EG, OVL>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
+    radix_onesweep_pipelined2_body<IPT, TIMING, SPLIT, PACK, 0, EG, OVL, LATE>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
                                                                 status_next, follow_plan, nullptr, nullptr, nullptr);
 }
 

@@ -11,22 +11,30 @@
 // tile's global prefix is known, and the round-1 kernel resolves that prefix one iteration late on purpose
 // (decoupled look-back without waiting).  The way out is the one on-chip memory round 1 left idle:
 //
-//   iteration j of a persistent CTA (t = the tile ranked now, p = the tile ranked an iteration ago)
-//     R  rank t      keys (loaded an iteration ago) -> one shared-memory atomicAdd per key -> keys and ranks
-//                    are PARKED IN TENSOR MEMORY (tcgen05.st, 32 lanes x 32 columns per warp, lane-private:
-//                    exactly the access pattern of key[IPT]); the loads of the next tile go out at once.
-//     D  digit work  group A: t's digit counts -> publish (two-level status rows, as in round 1);
-//                    group B: p's prefix by look-back (everything it needs was published an iteration ago),
-//                             then p's staging layout: every digit run starts at a shared-memory word that
-//                             is congruent mod 4 to its first DESTINATION word.
-//     S  stage p     keys and ranks come back from tensor memory (tcgen05.ld) and go to their staged words.
-//     W  write p     per digit run ONE bulk copy shared -> global for the 16-byte aligned interior
-//                    (cp.async.bulk.global.shared::cta, thread = digit), the <= 3 + 3 words before and
-//                    after it by ordinary stores.  (Byte-masked bulk copies for those edges measured 12.7
-//                    cycles each: three times slower than the stores.)
+//   iteration j of a persistent CTA (16 warps, 2 CTAs per SM, 10240-key tiles by ticket; t = the tile ranked
+//   now, p = the tile ranked an iteration ago):
+//        prefetch   ONE thread asks the TMA unit for the status rows of p's look-back: the earlier tile rows of
+//                   p's group and the nearest group rows are contiguous, so that is two bulk loads
+//                   (cp.async.bulk.shared::cta.global + mbarrier) that land underneath the ranking.
+//     R  rank t     keys (loaded an iteration ago) -> one shared-memory atomicAdd per key -> keys and ranks are
+//                   PARKED IN TENSOR MEMORY (tcgen05.st, 32 lanes x 32 columns per warp, lane-private: exactly
+//                   the access pattern of key[IPT]).
+//     D  digit work group A (thread = digit): t's digit counts -> publish (two-level status rows, as round 1);
+//                   group B (thread = digit): p's prefix summed from the prefetched rows (everything it needs
+//                   was published an iteration ago), then p's staging layout: every digit run starts at a
+//                   shared-memory word that is congruent mod 4 to its first DESTINATION word.
+//     S  stage p    keys and ranks come back from tensor memory (tcgen05.ld) and go to their staged words.
+//     W  write p    the next tile's loads go out; then per digit run ONE bulk copy shared -> global for the
+//                   16-byte aligned interior (cp.async.bulk.global.shared::cta, thread = digit), the <= 3 + 3
+//                   words before and after it by ordinary stores.  (Byte-masked bulk copies for those edges
+//                   measured 12.7 cycles each: three times slower than the stores.)
+//   The ticket of the next tile is drawn AFTER the digit work (the one phase whose length varies), so that from
+//   ticket to publication every tile takes the same stage + write + rank time and tiles are published in very
+//   nearly ticket order whatever the skew between CTAs.  (Tickets drawn two tiles ahead measured a full
+//   iteration of extra look-back waiting -- a convoy: profiles/r02_onesweep_variants.md.)
 //
 // Per 32 keys the load/store pipe now sees: global load 1, rank atomic ~3.6, position lookup ~3.3, staging
-// store ~3.7, digit work ~0.8, run edges ~2 (~14.5 in total), and the staging area is single instead of
+// store ~3.7, digit work ~1, run edges ~2 (~14.5 in total), and the staging area is single instead of
 // double (the bulk copies of tile p are done reading it long before tile p+1 is staged).
 #pragma once
 #include "radix_pipelined.cuh"
@@ -59,7 +67,7 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&r)[2]) {
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---- 1-D bulk copy shared -> global ------------------------------------------------------------------------
+// ---- 1-D bulk copies (TMA) ------------------------------------------------------------------------------------
 __device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
 }
@@ -67,26 +75,37 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void cp_async_16(uint32_t sdst, const void *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sdst), "l"(gsrc) : "memory");
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
 }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                 :: "r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(const uint32_t *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ void sts128(uint32_t *p, uint4 v) { *reinterpret_cast<uint4 *>(p) = v; }
 
-// Walk back over status rows like walk_back, the nearest `have` of them already sitting in shared memory
-// (win[(d-1)*256] = the row at distance d, for my digit).  A row that was not published yet when it was
-// fetched is polled in global memory.
+// Walk back over status rows like walk_back, the nearest `have` of them already sitting in shared memory in
+// memory order (win[(have - d) * 256] = the row at distance d, for my digit); eight loads in flight.  A word
+// that was not published yet when it was fetched is polled in global memory.
 template <int W>
 __device__ __forceinline__ uint32_t walk_back_prefetched(const uint32_t *win, uint32_t have, const uint32_t *first,
                                                          uint32_t max_dist) {
     uint32_t acc = 0;
-    const uint32_t lim = have < max_dist ? have : max_dist;
-    for (uint32_t base = 0; base < lim; base += 8) {
-        uint32_t w[8];                                           // eight independent shared-memory loads in flight
+    for (uint32_t base = 0; base < have; base += 8) {
+        uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = (base + j < lim) ? win[(base + j) * kRadixBins] : 0xFFFFFFFFu;
+        for (int j = 0; j < 8; ++j) w[j] = (base + j < have) ? win[(have - 1 - base - j) * kRadixBins] : 0u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (base + j < lim) {
+            if (base + j < have) {
                 uint32_t x = w[j];
                 while ((x & ~kValueMask) == 0) x = ld_relaxed_gpu(first - (size_t)(base + j) * kRadixBins);
                 acc += x & kValueMask;
@@ -94,7 +113,7 @@ __device__ __forceinline__ uint32_t walk_back_prefetched(const uint32_t *win, ui
             }
         }
     }
-    if (max_dist > lim) acc += walk_back<W>(first - (size_t)lim * kRadixBins, max_dist - lim);
+    if (max_dist > have) acc += walk_back<W>(first - (size_t)have * kRadixBins, max_dist - have);
     return acc;
 }
 
@@ -139,7 +158,7 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
     uint32_t *s_gprev  = s_pin + 2 * kRadixBins;                 // [256] the previous tile's prefix over the earlier groups
     uint32_t *s_win1   = s_gprev + kRadixBins;                   // [kTmaWin1][256] tile rows before the previous tile
     uint32_t *s_win2   = s_win1 + kTmaWin1 * kRadixBins;         // [kTmaWin2][256] group rows before its group
-    uint32_t *s_misc   = s_win2 + kTmaWin2 * kRadixBins;         // [0..7] warp sums, [8] ticket, [10] tmem base
+    uint32_t *s_misc   = s_win2 + kTmaWin2 * kRadixBins;         // [0..7] warp sums, [8] ticket, [10] tmem base, [16..17] mbarrier
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t tiles = (n + kTile - 1) / kTile;
@@ -181,9 +200,11 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
         uint4 *z = reinterpret_cast<uint4 *>(s_table);
         for (uint32_t i = tid; i < 2 * kRows * kRadixBins / 4; i += kTmaThreads) z[i] = make_uint4(0, 0, 0, 0);
     }
+    const uint32_t mbar = smem_u32(&s_misc[16]);
     if (tid == 0) {
         s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
-        s_misc[9] = atomicAdd(&ctl->ticket[pass], 1u);
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -205,9 +226,9 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
         }
     };
 
-    // tickets are taken two tiles ahead so that the loads of the next tile can go out right after the ranking
-    uint32_t tile = s_misc[8], next = s_misc[9];
+    uint32_t tile = s_misc[8];
     uint32_t prev_tile = 0xFFFFFFFFu;
+    uint32_t win_parity = 0;
     __syncthreads();                                             // s_misc[8] is rewritten inside the loop
     if (tile < tiles) load_tile(tile);
     const uint32_t digit_base = in_a ? 0u : ctl->base[pass][bd];
@@ -222,30 +243,20 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
         const uint32_t dbg_tile = have_cur ? tile : prev_tile;
         if (TIMING) { asm volatile("" :: "r"(key[0]), "r"(key[IPT - 1])); }
         B200_STAMP(0);                                           // this tile's keys are in registers
-        // ---- the previous tile's look-back rows are fetched into shared memory underneath the ranking --------
-        // (16-byte cp.async.cg: L2 only, no registers held; every row it needs was published an iteration ago)
-        if (have_prev && !in_a) {
+        // ---- the previous tile's look-back rows are fetched into shared memory underneath the ranking: the earlier
+        // tile rows of its group and the nearest group rows are contiguous, so that is two bulk loads ------------
+        uint32_t have1 = 0, have2 = 0;                           // rows fetched (tile rows, group rows)
+        if (have_prev) {
             const uint32_t group = prev_tile / kLookGroup, r = prev_tile % kLookGroup;
             const bool last_of_group = (r == kLookGroup - 1) || ((size_t)prev_tile + 1 == tiles);
-            const uint32_t chunk = bd & 63u, rsub = bd >> 6;
-            if (!last_of_group) {
-#pragma unroll
-                for (int i = 0; i < (kTmaWin1 + 3) / 4; ++i) {
-                    const uint32_t ri = i * 4 + rsub;            // distance - 1
-                    if (ri < r)
-                        cp_async_16(smem_u32(s_win1 + ri * kRadixBins + chunk * 4),
-                                    status_cur + ((size_t)prev_tile - 1 - ri) * kRadixBins + chunk * 4);
-                }
+            have1 = last_of_group ? 0u : r;
+            have2 = group < (uint32_t)kTmaWin2 ? group : (uint32_t)kTmaWin2;
+            if (tid == kRadixBins && have1 + have2 > 0) {
+                fence_proxy_async_smem();                        // last iteration's reads of the windows are done (SYNC2)
+                mbar_expect_tx(mbar, (have1 + have2) * kRadixBins * 4);
+                if (have1) bulk_load(smem_u32(s_win1), status_cur + ((size_t)prev_tile - have1) * kRadixBins, have1 * kRadixBins * 4, mbar);
+                if (have2) bulk_load(smem_u32(s_win2), status_cur + (tiles + group - have2) * kRadixBins, have2 * kRadixBins * 4, mbar);
             }
-            const uint32_t ng = group < (uint32_t)kTmaWin2 ? group : (uint32_t)kTmaWin2;
-#pragma unroll
-            for (int i = 0; i < (kTmaWin2 + 3) / 4; ++i) {
-                const uint32_t gi = i * 4 + rsub;
-                if (gi < ng)
-                    cp_async_16(smem_u32(s_win2 + gi * kRadixBins + chunk * 4),
-                                status_cur + (tiles + group - 1 - gi) * kRadixBins + chunk * 4);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
         }
         // ---- R: rank `tile`, park its keys and ranks in tensor memory ------------------------------------
         if (have_cur) {
@@ -287,13 +298,10 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
 #pragma unroll
             for (int i = 0; i < IPT; ++i) pk[tma_key_col(i)] = (uint32_t)key[i];
             tmem_st32(tmem_warp + cb * 128u, pk);                // completion is awaited before it is read back
-            // the next tile's loads go out now: they have the rest of the iteration to land
-            if (next < tiles) load_tile(next);
         }
         B200_STAMP(1);                                           // ranked and parked
         __syncthreads();                                         // SYNC1: `tile`'s counts are final
         B200_STAMP(2);
-        if (tid == 0) s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
 
         // ---- D: digit work, the two thread groups side by side ---------------------------------------------
         if (in_a) {
@@ -334,21 +342,20 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
                 const bool last_of_group = (r == kLookGroup - 1) || last_tile;
                 uint32_t *row = status_cur + (size_t)prev_tile * kRadixBins + bd;
                 uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
-                asm volatile("cp.async.wait_all;" ::: "memory");
-                bar_sync(2, kRadixBins);                         // the rows my group fetched are in shared memory
+                if (have1 + have2 > 0) { mbar_wait(mbar, win_parity); win_parity ^= 1; }   // the fetched rows have landed
                 B200_STAMP(11);
                 uint32_t inprev;
                 if (last_of_group) {
                     inprev = s_pin[pb * kRadixBins + bd];        // summed when the tile was published
                 } else {
-                    inprev = (r > 0) ? walk_back_prefetched<W>(s_win1 + bd, kTmaWin1, row - kRadixBins, r) : 0u;
+                    inprev = (r > 0) ? walk_back_prefetched<W>(s_win1 + bd, have1, row - kRadixBins, r) : 0u;
                     if (r > 0) st_relaxed_gpu(row, kFlagIncl | (inprev + p_total));   // shortens later walks
                 }
                 __syncwarp();                                    // the walk diverges per digit
                 B200_STAMP(12);
                 uint32_t gprev = 0;
                 if (group > 0) {
-                    gprev = walk_back_prefetched<W>(s_win2 + bd, kTmaWin2, grow - kRadixBins, group);
+                    gprev = walk_back_prefetched<W>(s_win2 + bd, have2, grow - kRadixBins, group);
                     if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + inprev + p_total) & kValueMask));
                 }
                 __syncwarp();                                    // the walks diverge per digit
@@ -390,7 +397,9 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
         bulk_wait_read_all();                                    // my bulk copies of the tile before are done READING the staging area
         __syncthreads();                                         // SYNC2: the previous tile's positions are final
         B200_STAMP(4);
-        const uint32_t after = s_misc[8];                        // the ticket after `next`
+        // The next tile's ticket is drawn now, AFTER the one phase whose length varies: from ticket to publication
+        // every tile then takes the same stage + write + rank time (see the header).
+        if (tid == 0) s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
 
         // ---- S: stage the previous tile: keys and ranks come back from tensor memory ------------------------
         if (have_prev) {
@@ -429,6 +438,9 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
         B200_STAMP(5);                                           // staged
         __syncthreads();                                         // SYNC3: the staged tile is complete
         B200_STAMP(6);
+        // the next tile's loads go out now and land while the previous tile is written
+        const uint32_t next = s_misc[8];
+        if (next < tiles) load_tile(next);
 
         // ---- W: write the previous tile: interiors by bulk copy, edges by ordinary stores ------------------
         if (have_prev) {
@@ -462,7 +474,6 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
             g_phase_dbg[((size_t)dbg_tile * 2 + (warp >> 3)) * 16 + 9] = dbg_tile;
         prev_tile = have_cur ? tile : 0xFFFFFFFFu;
         tile = next;
-        next = after;
         ++iter;
     }
     bulk_wait_all();                                             // every bulk copy has landed

@@ -36,8 +36,7 @@ for grp, label in ((0, "group A (warp 0)"), (1, "group B (warp 8)")):
         print(f"  {names[i-1]:>18s} -> {names[i]:<18s} mean {dt.mean():8.0f} cyc   p50 {np.median(dt):8.0f}   p90 {np.percentile(dt, 90):8.0f}")
     tot = mid[:, grp, 7] - mid[:, grp, 0]
     print(f"  iteration (keys in regs -> prev written) mean {tot.mean():.0f} cyc ({tot.mean()/1.965e3:.2f} us)")
-for a, b2, label in ((2, 11, "SYNC1 -> fetched rows landed (cp.async wait + group barrier)"), (11, 12, "walk over the tile rows"), (12, 10, "walk over the group rows")):
+
+for a, b2, label in ((2, 11, "SYNC1 -> fetched rows landed (mbarrier)"), (11, 12, "sum over the tile rows"), (12, 10, "sum over the group rows"), (10, 3, "staging layout + counters -> positions")):
     dt = mid[:, 1, b2] - mid[:, 1, a]
-    print(f"group B: {label:<62s} mean {dt.mean():8.0f} cyc   p50 {np.median(dt):8.0f}   p90 {np.percentile(dt, 90):8.0f}   max {dt.max():8.0f}")
-dt = mid[:, 1, 3] - mid[:, 1, 10]
-print(f"group B: resolved -> staging layout done  mean {dt.mean():8.0f} cyc   p50 {np.median(dt):8.0f}   p90 {np.percentile(dt, 90):8.0f}")
+    print(f"group B: {label:<48s} mean {dt.mean():8.0f} cyc   p50 {np.median(dt):8.0f}   p90 {np.percentile(dt, 90):8.0f}   max {dt.max():8.0f}")
