@@ -37,16 +37,23 @@ METRIC = "32-bit keys sorted/sec at n=2^28"
 UNIT = "keys/s"
 
 
-def _ncu_traffic(kernel_substr: str):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full summary
-    (profiles/rNN_ncu_*.json, written by tools/ncu_summary.py), or None."""
+def _ncu_traffic(kernel_substr: str, variant: str | None = None):
+    """DRAM bytes per launch of the dominant kernel from the newest committed ncu --set full summary
+    (profiles/rNN_ncu_*.json, written by tools/ncu_summary.py --json), or None.  A summary that names the
+    shape it was captured on (`variant`) is only used while that shape is still the one being launched, so the
+    figure cannot go stale when the kernel changes."""
     import glob
     best = None
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*.json"))):
         try:
             for item in json.load(open(path)):
                 if kernel_substr in item.get("kernel", "") and "dram_bytes_total" in item:
-                    best = {"bytes": item["dram_bytes_total"], "source": os.path.relpath(path, ROOT)}
+                    if variant is not None and item.get("variant") not in (None, variant):
+                        continue
+                    if variant is not None and item.get("variant") is None and os.path.basename(path).startswith("r01_"):
+                        continue                          # round 1's capture: a different kernel
+                    best = {"bytes": item["dram_bytes_total"], "source": os.path.relpath(path, ROOT),
+                            "variant": item.get("variant")}
                     try:     # the pipe that actually bounds these kernels (DESIGN.md section 7)
                         best["lsu_pct"] = float(item["LSU wavefronts % of peak"].split()[0])
                     except Exception:
@@ -400,7 +407,10 @@ def ours_single(args) -> None:
         dominant = "merge_pass_kernel (+ its partition kernel; one merge pass: 8 B/key)"
         algo_bytes_total = 8.0 * n * (1 + passes)
     achieved = bytes_per_launch / (kernel_ms / 1e3) / 1e9
-    traffic = _ncu_traffic("radix_onesweep" if algo == ALGO_RADIX else "merge_pass") if args.log2n == 28 else None
+    traffic = None
+    if args.log2n == 28:
+        traffic = (_ncu_traffic("radix_onesweep", L.b200sort_radix_effective_variant_name().decode()) if algo == ALGO_RADIX
+                   else _ncu_traffic("merge_pass"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic["bytes"] if traffic else None,
                 "traffic_source": traffic["source"] if traffic else None,

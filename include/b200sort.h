@@ -53,7 +53,9 @@ extern "C" {
 #define B200SORT_ALGO_MERGE         1   /* register bitonic block sort + merge-path merges */
 #define B200SORT_ALGO_LAB           2   /* the assignment's staged pipeline (radix tiles -> merges) */
 
-/* Largest n any entry point accepts (tile-status words carry 30-bit counts). */
+/* Largest n any entry point accepts (tile-status words carry 30-bit counts; a digit count can reach 2^30 only
+ * when one bin holds every key, which pass skipping removes -- with b200sort_radix_set_skip(0) the radix
+ * sorts therefore refuse n = 2^30 with B200SORT_ERR_INVALID). */
 #define B200SORT_MAX_N              ((size_t)1 << 30)
 
 const char *b200sort_version(void);
@@ -61,7 +63,10 @@ const char *b200sort_status_string(int status);
 /* cudaError_t (as int) of the most recent failing CUDA call on this host thread, 0 if none. */
 int         b200sort_last_cuda_error(void);
 const char *b200sort_last_cuda_error_string(void);
-/* B200SORT_OK iff the current device exists and is compute capability 10.x. */
+/* B200SORT_OK iff the current device exists and is compute capability 10.x.  Also the explicit per-device
+ * initialisation: runs the lane-order self-test of the radix sort for the current device if it has not run
+ * yet (allocates, launches on a private stream, BLOCKS).  Call it once per device before capturing CUDA
+ * graphs or timing: the first sort on a device otherwise does it lazily. */
 int         b200sort_device_check(void);
 
 /* ---- device-array sorts (the layer measured against the HBM roofline) --------------------------
@@ -72,6 +77,13 @@ int         b200sort_device_check(void);
  * Any n in [0, B200SORT_MAX_N]; the lab's n (power of two, multiple of 32) is the tested case,
  * ragged n is handled. */
 size_t b200sort_workspace_bytes(size_t n, int algo);
+/* b200sort_radix_i32: the default pass kernel ranks keys with ONE shared-memory atomicAdd per key, which is a
+ * stable rank only if the GPU resolves same-address lanes of one warp instruction in lane order.  B200 does
+ * (tools/atomic_order_probe.cu), PTX does not promise it.  GUARD: a self-test that reproduces the kernels'
+ * exact access pattern runs once per DEVICE -- in b200sort_device_check(), or lazily (blocking) in the first
+ * sort on that device -- and on failure, or with B200SORT_RANK_SAFE=1 in the environment, every radix entry
+ * point (keys, pairs, small arrays) runs the ballot-ranked shape of the same kernel instead, which relies on
+ * documented behaviour only.  b200sort_radix_atomic_order_ok() reports the verdict. */
 int    b200sort_radix_i32(int32_t *d_keys, int32_t *d_tmp, size_t n,
                           void *d_ws, size_t ws_bytes, void *stream);
 int    b200sort_merge_i32(int32_t *d_keys, int32_t *d_tmp, size_t n,
@@ -81,8 +93,7 @@ int    b200sort_merge_i32(int32_t *d_keys, int32_t *d_tmp, size_t n,
  * whole sort; with values 0..n-1 the result is the index permutation the doc comment at
  * SRM/lab.cu:44-45 ("positions") had in mind.  The onesweep passes with the value riding beside the key
  * (16 B/key per pass).  Workspace: b200sort_workspace_bytes(n, B200SORT_ALGO_RADIX).  The _copy form
- * leaves the inputs untouched.  Needs the lane-ordered atomics (b200sort_radix_atomic_order_ok() == 1);
- * returns B200SORT_ERR_INVALID otherwise. */
+ * leaves the inputs untouched.  Falls back to the ballot-ranked shape like b200sort_radix_i32. */
 int    b200sort_radix_pairs_i32(int32_t *d_keys, int32_t *d_vals, int32_t *d_tmp_keys, int32_t *d_tmp_vals,
                                 size_t n, void *d_ws, size_t ws_bytes, void *stream);
 int    b200sort_radix_pairs_copy_i32(const int32_t *d_keys_in, const int32_t *d_vals_in, int32_t *d_keys_out,
@@ -141,11 +152,9 @@ size_t      b200sort_radix_tile(void);            /* keys per onesweep tile of t
 int         b200sort_merge_set_variant(int variant);
 int         b200sort_merge_num_variants(void);
 const char *b200sort_merge_variant_name(int variant);
-/* The fastest tile shapes rank keys with one shared-memory atomicAdd per key, which is a stable
- * rank only if the GPU resolves same-address lanes of one warp instruction in lane order.  That is
- * observed on B200 but not promised by PTX, so the library runs a self-test once per process
- * (BLOCKS on first call; needs a device) and otherwise launches the ballot-ranked shape instead.
- * Returns 1 (ordered: fast shapes in use) or 0.  B200SORT_RANK_SAFE=1 in the environment forces 0. */
+/* Verdict of the lane-order self-test for the CURRENT device (see b200sort_radix_i32): 1 = ordered, the
+ * atomicAdd-ranked shapes are in use; 0 = the ballot-ranked shapes are.  Runs the test if it has not run on
+ * this device yet (BLOCKS).  B200SORT_RANK_SAFE=1 in the environment forces 0. */
 int         b200sort_radix_atomic_order_ok(void);
 /* Profiling aid: TIMING_* shapes stamp clock64() at their phase boundaries into this device buffer
  * (grid x 2 x 10 int64); NULL switches the probe off.  tools/phase_timing.py reads it. */

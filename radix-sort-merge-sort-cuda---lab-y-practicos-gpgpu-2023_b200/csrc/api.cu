@@ -374,7 +374,11 @@ const char *b200sort_status_string(int status) {
 
 int b200sort_last_cuda_error(void) { return (int)g_last_cuda_error; }
 const char *b200sort_last_cuda_error_string(void) { return cudaGetErrorString(g_last_cuda_error); }
-int b200sort_device_check(void) { return device_check(); }
+int b200sort_device_check(void) {
+    B200_TRY(device_check());
+    (void)radix_atomic_order_ok();      // explicit per-device initialisation: the lane-order self-test (blocks once)
+    return B200SORT_OK;
+}
 
 size_t b200sort_workspace_bytes(size_t n, int algo) { return workspace_bytes(n, algo); }
 

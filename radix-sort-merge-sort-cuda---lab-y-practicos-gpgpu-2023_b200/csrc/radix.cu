@@ -89,17 +89,21 @@ struct Variant {
 
 const Variant kVariants[] = {
     // ---- the shipped shapes ------------------------------------------------------------------------------------
-    B200_PP2X_VARIANT(20, 0, 1),               //  0: DEFAULT: persistent CTAs, 10240-key tiles, delayed two-level look-back,
-                                               //     16-bit counters (two warps per row), write-out by the load/store pipe
+    { "pipelined2_16w_ipt20_kRankAdd_pack1_late_ticket", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
+      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1> },   //  0: DEFAULT: persistent
+                                               //     CTAs, 10240-key tiles, delayed two-level look-back, 16-bit counters (two
+                                               //     warps per row), ticket drawn after the look-back, write-out by the
+                                               //     load/store pipe
     { "tma_16w_ipt20_kRankAdd_tmem_parked_bulk_store", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes,
       radix_onesweep_tma_kernel<0> },          //  1: keys parked in tensor memory, late co-aligned staging, TMA write-out
-    B200_VARIANT(16, 16, 2, kRankBallot, 1),   //  2: the documented-behaviour fallback (ballot-ranked, one tile per CTA)
+    { "pipelined2_16w_ipt20_kRankBallot_pack1_late_ticket", kRankBallot, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
+      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 1> },   //  2: the documented-
+                                               //     behaviour fallback: the default kernel ranked by ballots
     { "TIMING_tma_16w_ipt20", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes, radix_onesweep_tma_kernel<1> },   //  3
     { "TIMING_pipelined2_ipt20_pack", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
-      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 1, 0, 1> },   //  4
-    { "pipelined2_16w_ipt20_kRankAdd_pack1_late_ticket", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
-      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1> },   //  5: variant 0 with the
-                                               //     ticket drawn after the look-back
+      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 1, 0, 1, 2, 0, 0, 1> },   //  4
+    B200_PP2X_VARIANT(20, 0, 1),               //  5: variant 0 with the ticket drawn before the look-back (round 1's default)
+    B200_VARIANT(16, 16, 2, kRankBallot, 1),   //  6: one tile per CTA, ballot-ranked (round 1's fallback)
 #ifdef B200SORT_EXPERIMENTS
     // ---- every other shape measured in rounds 1-2 (profiles/r01_onesweep_variants.md): make EXPERIMENTS=1 ----------
     B200_PP2X_VARIANT(20, 0, 1),               //  0: DEFAULT (fastest measured, 0.712 ms/pass): persistent CTAs,
@@ -395,6 +399,9 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
         return B200SORT_OK;
     }
     B200_TRY(check_ws(d_ws, ws_bytes, n));
+    // Status words carry 30-bit counts.  A digit count reaches 2^30 only if n = 2^30 and one bin holds every key,
+    // which is exactly the case pass skipping removes: with skipping switched off that size is refused.
+    if (n >= ((size_t)1 << 30) && !g_skip_enabled.load()) return B200SORT_ERR_INVALID;
     // k0: up to 8192 keys are sorted by one CTA in one launch (untimed calls only: the timed form reports
     // the pipeline's kernels).  Same lane-ordered atomic rank as the pass kernel, same gate.
     if (ms == nullptr && n <= (size_t)kSmallTile && g_small_enabled.load() && atomic_order_ok()) {
@@ -456,11 +463,11 @@ int radix_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, vo
 // pass is (that is what makes LSD correct in the first place): equal keys keep their input order,
 // the A-before-B rule of SRM/lab.cu:163-170 carried through the whole sort.
 // Pairs per thread: 10 (default) or 12 (B200SORT_PAIRS_IPT=12, for A/B).
-template <int IPT>
+template <int IPT, int SAFE>
 int launch_pairs_passes(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const int32_t *v_in, int32_t *v_out,
                         int32_t *v_tmp, size_t n, RadixControl *ctl, uint32_t *const *status, cudaStream_t s) {
     constexpr size_t smem = Pipelined2Shape<IPT, 1, 1>::kSmemBytes;
-    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_onesweep_pairs_kernel<IPT>),
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_onesweep_pairs_kernel<IPT, SAFE>),
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t tiles = div_up(n, (size_t)Pipelined2Shape<IPT, 1, 1>::kTile);
     const unsigned slots = 2u * kNumSMs;
@@ -468,7 +475,7 @@ int launch_pairs_passes(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, con
     for (int pass = 0; pass < kRadixPasses; ++pass) {
         uint32_t *cur = status[pass & 1];
         uint32_t *next = (pass + 1 < kRadixPasses) ? status[(pass + 1) & 1] : nullptr;
-        radix_onesweep_pairs_kernel<IPT><<<grid, 512, smem, s>>>(d_in, d_out, d_tmp, n, pass, ctl, cur, next, 1,
+        radix_onesweep_pairs_kernel<IPT, SAFE><<<grid, 512, smem, s>>>(d_in, d_out, d_tmp, n, pass, ctl, cur, next, 1,
                                                                 v_in, v_out, v_tmp);
         B200_LAUNCH_CHECK();
     }
@@ -478,7 +485,7 @@ int pairs_ipt() {
     static const int v = [] { const char *e = getenv("B200SORT_PAIRS_IPT"); return (e && atoi(e) == 12) ? 12 : 10; }();
     return v;
 }
-size_t radix_pairs_tile() { return 512u * (size_t)pairs_ipt(); }
+size_t radix_pairs_tile() { return 512u * (size_t)(atomic_order_ok() ? pairs_ipt() : 10); }
 
 int radix_sort_pairs(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const int32_t *v_in, int32_t *v_out,
                      int32_t *v_tmp, size_t n, void *d_ws, size_t ws_bytes, cudaStream_t s) {
@@ -490,7 +497,8 @@ int radix_sort_pairs(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const 
     }
     if ((d_in == d_out) != (v_in == v_out)) return B200SORT_ERR_INVALID;   // the plan is shared by keys and values
     B200_TRY(check_ws(d_ws, ws_bytes, n));
-    if (!atomic_order_ok()) return B200SORT_ERR_INVALID;                   // no ballot-ranked pairs shape is compiled
+    if (n >= ((size_t)1 << 30) && !g_skip_enabled.load()) return B200SORT_ERR_INVALID;   // see radix_sort_impl
+    const bool safe = !atomic_order_ok();                                  // then the ballot-ranked shape runs
     B200_TRY(ensure_hist_attr());
     auto *ctl = static_cast<RadixControl *>(d_ws);
     const size_t tiles = div_up(n, radix_pairs_tile());
@@ -505,8 +513,9 @@ int radix_sort_pairs(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const 
     radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_in, n, ctl, status[0], rows * kRadixBins,
                                                                  (uint32_t)skip, in_place);
     B200_LAUNCH_CHECK();
-    if (pairs_ipt() == 12) B200_TRY(launch_pairs_passes<12>(d_in, d_out, d_tmp, v_in, v_out, v_tmp, n, ctl, status, s));
-    else                   B200_TRY(launch_pairs_passes<10>(d_in, d_out, d_tmp, v_in, v_out, v_tmp, n, ctl, status, s));
+    if (safe)                   B200_TRY((launch_pairs_passes<10, 1>(d_in, d_out, d_tmp, v_in, v_out, v_tmp, n, ctl, status, s)));
+    else if (pairs_ipt() == 12) B200_TRY((launch_pairs_passes<12, 0>(d_in, d_out, d_tmp, v_in, v_out, v_tmp, n, ctl, status, s)));
+    else                        B200_TRY((launch_pairs_passes<10, 0>(d_in, d_out, d_tmp, v_in, v_out, v_tmp, n, ctl, status, s)));
     if (skip) {
         const size_t blocks = div_up(div_up(n, 4), 256);
         const unsigned g2 = (unsigned)(blocks < (size_t)kNumSMs * 8 ? blocks : (size_t)kNumSMs * 8);

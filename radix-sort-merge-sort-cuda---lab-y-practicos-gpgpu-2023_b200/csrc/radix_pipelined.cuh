@@ -368,7 +368,9 @@ struct Pipelined2Shape {
 // OVL  : no CTA barrier between the digit phase and the staging.  Group A stages as soon as ITS positions
 //        are final; group B walks the previous tile's tile rows, sends the first window of group-row loads
 //        off, stages while they fly, then finishes the walk.  One CTA barrier before the write-out.
-template <int IPT, int TIMING, int SPLIT, int PACK, int KV, int EG = 0, int OVL = 0, int LATE = 0>
+// SAFE : rank with eight __ballot_sync per key and ONE atomic per distinct digit of the warp instruction (documented
+//        behaviour only) instead of one atomic per key (which needs same-address lanes to be resolved in lane order).
+template <int IPT, int TIMING, int SPLIT, int PACK, int KV, int EG = 0, int OVL = 0, int LATE = 0, int SAFE = 0>
 __device__ __forceinline__ void
 radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
@@ -597,7 +599,25 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
             // a locally hot one (a quarter of the warp's first keys agree with lane 0's: sorted input)
             const uint32_t hot_word = follow_plan ? ctl->hot[pass] : 0u;
             const bool hot = hot_word != 0 || __popc(agree) >= 8;
-            if (!hot) {
+            if (SAFE) {
+#pragma unroll
+                for (int i = 0; i < IPT; ++i) {
+                    const uint32_t d = digit_of(key[i], shift, flip);
+                    uint32_t peers = 0xffffffffu;                 // lanes of this instruction that hold my digit
+#pragma unroll
+                    for (int bit = 0; bit < kRadixBits; ++bit) {
+                        const bool one = (d >> bit) & 1u;
+                        const uint32_t vote = __ballot_sync(0xffffffffu, one);
+                        peers &= one ? vote : ~vote;
+                    }
+                    const uint32_t lower = peers & lt;
+                    uint32_t before = 0;
+                    if (lower == 0) before = my_half(atomicAdd(wt + d, (uint32_t)__popc(peers) << sh));   // one lane per digit
+                    before = __shfl_sync(0xffffffffu, before, __ffs(peers) - 1);
+                    const uint32_t r = before + __popc(lower);
+                    rank2[i / 2] = (i & 1) ? (rank2[i / 2] | (r << 16)) : r;
+                }
+            } else if (!hot) {
 #pragma unroll
                 for (int i = 0; i < IPT; ++i) {
                     const uint32_t r = my_half(atomicAdd(wt + digit_of(key[i], shift, flip), 1u << sh));
@@ -807,24 +827,24 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
 }
 
 // MINB: CTAs per SM the register allocation is held to (3 with tiles of <= 6144 keys: 40 registers).
-template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0, int MINB = 2, int EG = 0, int OVL = 0, int LATE = 0>
+template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0, int MINB = 2, int EG = 0, int OVL = 0, int LATE = 0, int SAFE = 0>
 __global__ void __launch_bounds__(512, MINB)
 radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                  int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
                                  int follow_plan)
 {
-    radix_onesweep_pipelined2_body<IPT, TIMING, SPLIT, PACK, 0, EG, OVL, LATE>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
+    radix_onesweep_pipelined2_body<IPT, TIMING, SPLIT, PACK, 0, EG, OVL, LATE, SAFE>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
                                                                 status_next, follow_plan, nullptr, nullptr, nullptr);
 }
 
 // Sort-by-key: the same pass with a 32-bit value riding along with every key.
-template <int IPT>
+template <int IPT, int SAFE = 0>
 __global__ void __launch_bounds__(512, 2)
 radix_onesweep_pairs_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                             int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
                             int follow_plan, const int32_t *in_vals, int32_t *out_vals, int32_t *tmp_vals)
 {
-    radix_onesweep_pipelined2_body<IPT, 0, 0, 1, 1>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
+    radix_onesweep_pipelined2_body<IPT, 0, 0, 1, 1, 0, 0, 1, SAFE>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
                                                     status_next, follow_plan, in_vals, out_vals, tmp_vals);
 }
 

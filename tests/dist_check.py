@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N tests/dist_2gpu_check.py : the real multi-GPU path (both exchange
+"""torchrun --nproc-per-node N tests/dist_check.py : the real multi-GPU path (both exchange
 modes) checked against a gathered host sort.  Run under `gpurun --gpus N`."""
 import os
 import sys
