@@ -511,6 +511,8 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 2-5 rows")
     ap.add_argument("--config-steps", type=int, default=4, help="timed sorts per row of the configs block")
+    ap.add_argument("--total-log2n", type=int, default=None,
+                    help="multi-GPU: 2^T keys IN TOTAL split over the ranks (strong scaling; BASELINE config 5: 30)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU exchange: fused peer-write scatter (default) or NCCL all-to-all")
     args = ap.parse_args()

@@ -198,7 +198,7 @@ int  b200sort_host_free_pinned(void *h_ptr);
  *                                        (then the scatter IS the exchange, over NVLink)
  * Phase 4  b200sort_sort_copy_i32        local sort of what arrived */
 #define B200SORT_DIST_BITS_MIN 4
-#define B200SORT_DIST_BITS_MAX 12
+#define B200SORT_DIST_BITS_MAX 14
 #define B200SORT_DIST_MAX_WORLD 16
 /* d_hist: uint64[2^bits], overwritten. */
 int b200sort_dist_histogram_i32(const int32_t *d_keys, size_t n, int bits,
@@ -224,6 +224,23 @@ int b200sort_dist_partition_i32(const int32_t *d_keys, size_t n, int bits, int w
                                 int32_t *const *h_dst_base, const int *d_bin_owner,
                                 const unsigned long long *h_dst_offset,
                                 void *d_ws, size_t ws_bytes, void *stream);
+/* The same without a host synchronisation.  The planner runs on the device over the all-gathered counts
+ * (d_all_hist, world x 2^bits uint64 in DEVICE memory) and leaves its result in a device record d_plan
+ * (B200SORT_DIST_PLAN_BYTES, 8-byte aligned): recv_count[16], send_count[16], dst_offset[16] (uint64 each), then
+ * uint32 m = the number of keys this rank will own, uint32 error = 1 if some rank would receive more than `cap`
+ * keys (then the partition kernel writes nothing).  Same boundaries as b200sort_dist_plan, bit for bit.
+ * b200sort_dist_partition_planned_i32 takes its offsets from that record, and b200sort_radix_copy_devn_i32 sorts
+ * what arrived with the key count read from device memory (d_n = the record's m; n_max sizes grids and workspace),
+ * so a whole distributed sort is enqueued without the host ever reading a count. */
+#define B200SORT_DIST_PLAN_BYTES 400
+int b200sort_dist_plan_device(const unsigned long long *d_all_hist, int world, int rank, int bits,
+                              unsigned long long cap, int *d_bin_owner, void *d_plan,
+                              void *d_ws, size_t ws_bytes, void *stream);
+int b200sort_dist_partition_planned_i32(const int32_t *d_keys, size_t n, int bits, int world,
+                                        int32_t *const *h_dst_base, const int *d_bin_owner, const void *d_plan,
+                                        void *d_ws, size_t ws_bytes, void *stream);
+int b200sort_radix_copy_devn_i32(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n_max,
+                                 const uint32_t *d_n, void *d_ws, size_t ws_bytes, void *stream);
 /* Plain cudaMalloc / cudaFree (receive buffers must be whole allocations to be exported) and the
  * CUDA IPC plumbing that lets ranks (separate processes) map each other's receive buffers. */
 #define B200SORT_IPC_HANDLE_BYTES 64

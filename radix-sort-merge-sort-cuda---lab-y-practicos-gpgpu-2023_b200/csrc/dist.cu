@@ -70,7 +70,8 @@ dist_histogram_kernel(const int32_t *__restrict__ keys, size_t n, int bits, unsi
 // ------------------------------------------------------------------------------------------------
 struct DistPartitionArgs {
     int32_t *dst_base[kDistMaxWorld];                  // receive buffer of every rank
-    unsigned long long dst_offset[kDistMaxWorld];      // where this rank's block starts in it
+    unsigned long long dst_offset[kDistMaxWorld];      // where this rank's block starts in it (host plan)
+    const DistPlanDev *plan;                           // non-null: offsets (and the error flag) come from the device plan
 };
 
 // Staging area: the tile's keys grouped by destination, with up to 3 pad slots in front of every
@@ -85,7 +86,11 @@ __device__ __forceinline__ void st_stream_v4(int32_t *p, int4 v) {
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int THREADS, int OCC>
+// TMA: the interior of every destination group (whole 16-byte chunks: the staging is co-aligned) leaves with ONE
+// bulk copy shared -> global per destination and tile (cp.async.bulk.global.shared::cta; the destination may be
+// a peer-mapped buffer: the copy then crosses NVLink in large posted writes); group heads and tails (<= 3 + 3
+// words) by ordinary stores.
+template <int THREADS, int OCC, int TMA = 0>
 __global__ void __launch_bounds__(THREADS, OCC)
 dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int world,
                       const int *__restrict__ bin_owner, DistPartitionArgs args,
@@ -104,6 +109,7 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
     const uint32_t tid = threadIdx.x;
     const uint32_t nbins = 1u << bits;
     const int shift = 32 - bits;
+    if (args.plan != nullptr && args.plan->error) return;     // some receive buffer is too small: nobody writes
     for (uint32_t i = tid; i < nbins; i += THREADS) s_owner[i] = (uint8_t)bin_owner[i];
 
     const size_t tiles = (n + kTile - 1) / kTile;
@@ -111,8 +117,10 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
         const size_t base = tile * kTile;
         const uint32_t valid = (n - base < (size_t)kTile) ? (uint32_t)(n - base) : (uint32_t)kTile;
         if (tid < kDistMaxWorld) s_cnt[tid] = 0;
-        for (uint32_t i = tid; i < kSlots / 16; i += THREADS)         // every slot starts as a pad
-            reinterpret_cast<uint4 *>(s_dest)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (!TMA)
+            for (uint32_t i = tid; i < kSlots / 16; i += THREADS)     // every slot starts as a pad
+                reinterpret_cast<uint4 *>(s_dest)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (TMA) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // my bulk copies have read the staging area
         __syncthreads();                               // also: s_owner ready, previous tile drained
 
         int32_t key[kDistIpt];
@@ -132,7 +140,7 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
         }
         __syncthreads();
         if (tid < (uint32_t)world)                     // reserve this tile's share of every destination
-            s_gbase[tid] = args.dst_offset[tid] +
+            s_gbase[tid] = (args.plan != nullptr ? args.plan->dst_offset[tid] : args.dst_offset[tid]) +
                            (s_cnt[tid] ? atomicAdd(&cursor[tid], (unsigned long long)s_cnt[tid]) : 0ull);
         __syncthreads();
         if (tid == 0) {
@@ -152,8 +160,26 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
                 const uint32_t d = slot[i] >> 16;
                 const uint32_t q = s_start[d] + (slot[i] & 0xffffu);
                 s_keys[q] = key[i];
-                s_dest[q] = (uint8_t)d;
+                if (!TMA) s_dest[q] = (uint8_t)d;
             }
+        }
+        if (TMA) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid < (uint32_t)world) {
+                const uint32_t start = s_start[tid], c = s_cnt[tid];
+                int32_t *dst = args.dst_base[tid] + s_gbase[tid];            // element 0 of this tile's group
+                uint32_t head = (4u - ((uint32_t)s_gbase[tid] & 3u)) & 3u;
+                if (head > c) head = c;
+                const uint32_t body = (c - head) & ~3u;
+                if (body > 0)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(dst + head), "r"((uint32_t)__cvta_generic_to_shared(s_keys + start + head)), "r"(body * 4u) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                for (uint32_t e = 0; e < head; ++e) st_stream(dst + e, s_keys[start + e]);
+                for (uint32_t e = head + body; e < c; ++e) st_stream(dst + e, s_keys[start + e]);
+            }
+            continue;                                  // the loop head waits for the copies and synchronises
         }
         __syncthreads();
         const uint32_t vectors = (s_start[world] + 3) / 4;
@@ -175,10 +201,97 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
         }
         __syncthreads();                               // the staging area is reused by the next tile
     }
+    if (TMA) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// The planner.  Rank k's range ends at the bin boundary closest to k/world of the keys; exact integer
+// arithmetic, one function for the host planner (dist_plan) and the device planner (dist_plan_kernel), so that
+// they agree bit for bit.  cum[b] = keys in bins < b (cum[nbins] = total).
+__host__ __device__ inline uint32_t plan_boundary(const unsigned long long *cum, uint32_t nbins, uint32_t world, uint32_t k) {
+    const unsigned long long total = cum[nbins];
+    uint32_t lo = 0, hi = nbins;                       // first b with cum[b] * world >= total * k
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) / 2;
+        if (cum[mid] * world >= total * k) hi = mid; else lo = mid + 1;
+    }
+    if (lo > 0) {
+        // the bin that straddles the target goes to the NEXT rank if more than half of it lies beyond the target
+        const unsigned long long c0 = cum[lo - 1], g = cum[lo] - cum[lo - 1];
+        if (c0 > 0 && (2 * c0 + g) * world > 2 * total * k && (c0 + g) * world > total * k) return lo - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(1024)
+dist_plan_kernel(const unsigned long long *__restrict__ all_hist, uint32_t world, uint32_t rank, uint32_t nbins,
+                 unsigned long long cap, int *bin_owner, DistPlanDev *plan, unsigned long long *cum /* [nbins + 1] */)
+{
+    __shared__ unsigned long long s_part[32];
+    __shared__ uint32_t s_bound[kDistMaxWorld + 1];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // exclusive prefix sums of the global bin counts: every thread owns nbins / 1024 consecutive bins
+    const uint32_t per = (nbins + 1023) / 1024;
+    const uint32_t b0 = tid * per;
+    unsigned long long local = 0;
+    for (uint32_t j = 0; j < per && b0 + j < nbins; ++j)
+        for (uint32_t r = 0; r < world; ++r) local += all_hist[(size_t)r * nbins + b0 + j];
+    unsigned long long x = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) s_part[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = s_part[lane], z = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, z, o);
+            if (lane >= (uint32_t)o) z += y;
+        }
+        s_part[lane] = z - w;                          // exclusive over the warps
+    }
+    __syncthreads();
+    unsigned long long run = x - local + s_part[warp];
+    for (uint32_t j = 0; j < per && b0 + j < nbins; ++j) {
+        cum[b0 + j] = run;
+        for (uint32_t r = 0; r < world; ++r) run += all_hist[(size_t)r * nbins + b0 + j];
+    }
+    if (tid == 1023 || (b0 < nbins && b0 + per >= nbins)) cum[nbins] = run;   // the thread that owns the last bin
+    __threadfence_block();
+    __syncthreads();
+    if (tid <= world) s_bound[tid] = (tid == 0) ? 0u : (tid == world) ? nbins : plan_boundary(cum, nbins, world, tid);
+    __syncthreads();
+    for (uint32_t b = tid; b < nbins; b += 1024) {
+        uint32_t o = 0;
+        for (uint32_t k = 1; k < world; ++k) o += (s_bound[k] <= b) ? 1u : 0u;
+        bin_owner[b] = (int)o;
+    }
+    if (tid < world) {
+        const unsigned long long rc = cum[s_bound[tid + 1]] - cum[s_bound[tid]];
+        plan->recv_count[tid] = rc;
+        if (tid == rank) plan->m = (unsigned int)rc;
+        if (rc > cap) plan->error = 1u;                // host zeroes the record before the kernel
+    }
+    // this rank's block inside every destination: keys of the earlier ranks in that destination's range
+    for (uint32_t pair = warp; pair < (rank + 1) * world; pair += 32) {
+        const uint32_t src = pair / world, o = pair % world;
+        unsigned long long acc = 0;
+        for (uint32_t b = s_bound[o] + lane; b < s_bound[o + 1]; b += 32) acc += all_hist[(size_t)src * nbins + b];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) {
+            if (src == rank) plan->send_count[o] = acc;
+            else atomicAdd(&plan->dst_offset[o], acc);
+        }
+    }
 }
 
 // ================================================================================================
-size_t dist_workspace_bytes(size_t, int) { return 256; }    // the destination cursors
+// the destination cursors, then (device planner) the prefix sums of the global bin counts
+size_t dist_workspace_bytes(size_t, int bits) { return 256 + (((size_t)1 << bits) + 1) * sizeof(unsigned long long); }
 
 static size_t partition_smem(int bits, int threads) {
     const size_t slots = (size_t)threads * kDistIpt + 4 * kDistMaxWorld;
@@ -192,6 +305,9 @@ int dist_histogram(const int32_t *d_keys, size_t n, int bits, unsigned long long
     if (n == 0) return B200SORT_OK;
     const size_t want = div_up(div_up(n, 4), (size_t)kDistThreads * 4);
     const unsigned grid = (unsigned)(want < (size_t)kNumSMs * 3 ? (want ? want : 1) : (size_t)kNumSMs * 3);
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_histogram_kernel),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(((size_t)1 << B200SORT_DIST_BITS_MAX) * sizeof(uint32_t))));
     dist_histogram_kernel<<<grid, kDistThreads, nbins * sizeof(uint32_t), s>>>(d_keys, n, bits, d_hist);
     B200_LAUNCH_CHECK();
     return B200SORT_OK;
@@ -201,34 +317,23 @@ int dist_plan(const unsigned long long *all_hist, int world, int rank, int bits,
               unsigned long long *recv_count, unsigned long long *send_count,
               unsigned long long *dst_offset) {
     if (all_hist == nullptr || bin_owner == nullptr || world < 1 || world > kDistMaxWorld || rank < 0 ||
-        rank >= world || bits < 1 || bits > B200SORT_DIST_BITS_MAX)
+        rank >= world || bits < B200SORT_DIST_BITS_MIN || bits > B200SORT_DIST_BITS_MAX)
         return B200SORT_ERR_INVALID;
     const size_t nbins = (size_t)1 << bits;
-    std::vector<unsigned long long> global(nbins, 0);
-    unsigned long long total = 0;
+    std::vector<unsigned long long> global(nbins, 0), cum(nbins + 1, 0);
     for (int r = 0; r < world; ++r)
         for (size_t b = 0; b < nbins; ++b) { global[b] += all_hist[(size_t)r * nbins + b]; }
-    for (size_t b = 0; b < nbins; ++b) total += global[b];
+    for (size_t b = 0; b < nbins; ++b) cum[b + 1] = cum[b] + global[b];
 
-    // Contiguous bin ranges: rank r ends at the bin boundary closest to (r+1)/world of the keys.
-    // Owners are non-decreasing in the bin index, so the concatenation of the ranks' sorted
-    // outputs is globally sorted and signed order is kept (bins index key ^ 0x80000000).
-    unsigned long long cum = 0;
-    int owner = 0;
-    for (size_t b = 0; b < nbins; ++b) {
-        while (owner < world - 1) {
-            // keys that ranks 0..owner should hold together
-            const long double target = (long double)total * (owner + 1) / world;
-            // give bin b to the next rank if starting it here leaves `owner` closer to its target
-            if ((long double)cum >= target ||
-                ((long double)cum + (long double)global[b] / 2 > target && cum > 0 &&
-                 (long double)cum + (long double)global[b] > target))
-                ++owner;
-            else
-                break;
+    // Contiguous bin ranges: rank r ends at the bin boundary closest to (r+1)/world of the keys (plan_boundary, the
+    // function the device planner uses).  Owners are non-decreasing in the bin index, so the concatenation of the
+    // ranks' sorted outputs is globally sorted and signed order is kept (bins index key ^ 0x80000000).
+    {
+        size_t b = 0;
+        for (int k = 1; k <= world; ++k) {
+            const size_t end = (k == world) ? nbins : plan_boundary(cum.data(), (uint32_t)nbins, (uint32_t)world, (uint32_t)k);
+            for (; b < end; ++b) bin_owner[b] = k - 1;
         }
-        bin_owner[b] = owner;
-        cum += global[b];
     }
     if (recv_count) std::memset(recv_count, 0, sizeof(unsigned long long) * world);
     if (send_count) std::memset(send_count, 0, sizeof(unsigned long long) * world);
@@ -243,42 +348,71 @@ int dist_plan(const unsigned long long *all_hist, int world, int rank, int bits,
     return B200SORT_OK;
 }
 
-int dist_partition(const int32_t *d_keys, size_t n, int bits, int world, int32_t *const *h_dst_base,
-                   const int *d_bin_owner, const unsigned long long *h_dst_offset, void *d_ws,
-                   size_t ws_bytes, cudaStream_t s) {
+static int partition_launch(const int32_t *d_keys, size_t n, int bits, int world, int32_t *const *h_dst_base,
+                            const int *d_bin_owner, const unsigned long long *h_dst_offset, const DistPlanDev *d_plan,
+                            void *d_ws, size_t ws_bytes, cudaStream_t s) {
     if (bits < B200SORT_DIST_BITS_MIN || bits > B200SORT_DIST_BITS_MAX || world < 1 || world > kDistMaxWorld ||
-        h_dst_base == nullptr || h_dst_offset == nullptr || d_bin_owner == nullptr)
+        h_dst_base == nullptr || (h_dst_offset == nullptr && d_plan == nullptr) || d_bin_owner == nullptr)
         return B200SORT_ERR_INVALID;
-    if (d_ws == nullptr || ws_bytes < dist_workspace_bytes(n, bits)) return B200SORT_ERR_WORKSPACE;
-    for (int r = 0; r < world; ++r)       // 128-bit stores into the destinations
+    if (d_ws == nullptr || ws_bytes < 256) return B200SORT_ERR_WORKSPACE;
+    for (int r = 0; r < world; ++r)       // 128-bit stores / bulk copies into the destinations
         if (reinterpret_cast<uintptr_t>(h_dst_base[r]) & 15) return B200SORT_ERR_INVALID;
     if (n == 0) return B200SORT_OK;
     DistPartitionArgs args;
     std::memset(&args, 0, sizeof args);
-    for (int r = 0; r < world; ++r) { args.dst_base[r] = h_dst_base[r]; args.dst_offset[r] = h_dst_offset[r]; }
-    // Two compiled shapes: 512 threads x 2 CTAs/SM (8192-key tiles) and 256 threads x 4 CTAs/SM
-    // (4096-key tiles, more tiles in flight per SM).  B200SORT_DIST_SHAPE=1 selects the second.
+    for (int r = 0; r < world; ++r) { args.dst_base[r] = h_dst_base[r]; args.dst_offset[r] = h_dst_offset ? h_dst_offset[r] : 0; }
+    args.plan = d_plan;
+    // Compiled shapes: 512 threads x 2 CTAs/SM (8192-key tiles), write-out by bulk copies (default) or by 128-bit
+    // stores (B200SORT_DIST_TMA=0); 256 threads x 4 CTAs/SM with stores (B200SORT_DIST_SHAPE=1).
     static const int shape = [] { const char *e = getenv("B200SORT_DIST_SHAPE"); return (e && e[0] == '1') ? 1 : 0; }();
+    static const int tma = [] { const char *e = getenv("B200SORT_DIST_TMA"); return (e && e[0] == '0') ? 0 : 1; }();
     // function attributes are per device: set before every launch
-    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel<512, 2>),
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)partition_smem(B200SORT_DIST_BITS_MAX, 512)));
-    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel<256, 4>),
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)partition_smem(B200SORT_DIST_BITS_MAX, 256)));
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel<512, 2, 0>),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_smem(B200SORT_DIST_BITS_MAX, 512)));
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel<512, 2, 1>),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_smem(B200SORT_DIST_BITS_MAX, 512)));
+    B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel<256, 4, 0>),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_smem(B200SORT_DIST_BITS_MAX, 256)));
     auto *cursor = static_cast<unsigned long long *>(d_ws);
     B200_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long) * kDistMaxWorld, s));
     if (shape == 0) {
         const size_t tiles = div_up(n, (size_t)512 * kDistIpt);
         const unsigned grid = (unsigned)(tiles < (size_t)kNumSMs * 2 ? tiles : (size_t)kNumSMs * 2);
-        dist_partition_kernel<512, 2><<<grid, 512, partition_smem(bits, 512), s>>>(d_keys, n, bits, world, d_bin_owner,
-                                                                                  args, cursor);
+        if (tma) dist_partition_kernel<512, 2, 1><<<grid, 512, partition_smem(bits, 512), s>>>(d_keys, n, bits, world, d_bin_owner, args, cursor);
+        else     dist_partition_kernel<512, 2, 0><<<grid, 512, partition_smem(bits, 512), s>>>(d_keys, n, bits, world, d_bin_owner, args, cursor);
     } else {
         const size_t tiles = div_up(n, (size_t)256 * kDistIpt);
         const unsigned grid = (unsigned)(tiles < (size_t)kNumSMs * 4 ? tiles : (size_t)kNumSMs * 4);
-        dist_partition_kernel<256, 4><<<grid, 256, partition_smem(bits, 256), s>>>(d_keys, n, bits, world, d_bin_owner,
-                                                                                  args, cursor);
+        dist_partition_kernel<256, 4, 0><<<grid, 256, partition_smem(bits, 256), s>>>(d_keys, n, bits, world, d_bin_owner, args, cursor);
     }
+    B200_LAUNCH_CHECK();
+    return B200SORT_OK;
+}
+
+int dist_partition(const int32_t *d_keys, size_t n, int bits, int world, int32_t *const *h_dst_base,
+                   const int *d_bin_owner, const unsigned long long *h_dst_offset, void *d_ws,
+                   size_t ws_bytes, cudaStream_t s) {
+    if (h_dst_offset == nullptr) return B200SORT_ERR_INVALID;
+    return partition_launch(d_keys, n, bits, world, h_dst_base, d_bin_owner, h_dst_offset, nullptr, d_ws, ws_bytes, s);
+}
+
+int dist_partition_planned(const int32_t *d_keys, size_t n, int bits, int world, int32_t *const *h_dst_base,
+                           const int *d_bin_owner, const void *d_plan, void *d_ws, size_t ws_bytes, cudaStream_t s) {
+    if (d_plan == nullptr) return B200SORT_ERR_INVALID;
+    return partition_launch(d_keys, n, bits, world, h_dst_base, d_bin_owner, nullptr, static_cast<const DistPlanDev *>(d_plan),
+                            d_ws, ws_bytes, s);
+}
+
+int dist_plan_device(const unsigned long long *d_all_hist, int world, int rank, int bits, unsigned long long cap,
+                     int *d_bin_owner, void *d_plan, void *d_ws, size_t ws_bytes, cudaStream_t s) {
+    if (d_all_hist == nullptr || d_bin_owner == nullptr || d_plan == nullptr || world < 1 || world > kDistMaxWorld ||
+        rank < 0 || rank >= world || bits < B200SORT_DIST_BITS_MIN || bits > B200SORT_DIST_BITS_MAX)
+        return B200SORT_ERR_INVALID;
+    if (d_ws == nullptr || ws_bytes < dist_workspace_bytes(0, bits)) return B200SORT_ERR_WORKSPACE;
+    B200_CUDA_TRY(cudaMemsetAsync(d_plan, 0, sizeof(DistPlanDev), s));
+    auto *cum = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(d_ws) + 256);
+    dist_plan_kernel<<<1, 1024, 0, s>>>(d_all_hist, (uint32_t)world, (uint32_t)rank, 1u << bits, cap, d_bin_owner,
+                                        static_cast<DistPlanDev *>(d_plan), cum);
     B200_LAUNCH_CHECK();
     return B200SORT_OK;
 }

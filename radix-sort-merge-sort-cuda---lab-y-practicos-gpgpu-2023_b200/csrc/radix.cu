@@ -391,10 +391,11 @@ struct StepTimer {
 };
 
 int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, void *d_ws,
-                    size_t ws_bytes, cudaStream_t s, float *ms) {
+                    size_t ws_bytes, cudaStream_t s, float *ms, const uint32_t *d_n = nullptr) {
+    // d_n != nullptr: n is an upper bound (grids, status rows), the kernels read the key count from *d_n
     if (ms) for (int i = 0; i < 6; ++i) ms[i] = 0.f;
     if (n == 0) return B200SORT_OK;
-    if (n == 1) {
+    if (n == 1 && d_n == nullptr) {
         if (d_in != d_out) B200_CUDA_TRY(cudaMemcpyAsync(d_out, d_in, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
         return B200SORT_OK;
     }
@@ -404,7 +405,7 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
     if (n >= ((size_t)1 << 30) && !g_skip_enabled.load()) return B200SORT_ERR_INVALID;
     // k0: up to 8192 keys are sorted by one CTA in one launch (untimed calls only: the timed form reports
     // the pipeline's kernels).  Same lane-ordered atomic rank as the pass kernel, same gate.
-    if (ms == nullptr && n <= (size_t)kSmallTile && g_small_enabled.load() && atomic_order_ok()) {
+    if (ms == nullptr && d_n == nullptr && n <= (size_t)kSmallTile && g_small_enabled.load() && atomic_order_ok()) {
         B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(radix_small_kernel),
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemBytes));
         radix_small_kernel<<<1, kSmallThreads, kSmallSmemBytes, s>>>(d_in, d_out, (uint32_t)n);
@@ -428,13 +429,13 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
     B200_CUDA_TRY(cudaMemsetAsync(ctl, 0, kRadixZeroBytes, s));
     B200_TRY(timer.begin());
     radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_in, n, ctl, status[0], rows * kRadixBins,
-                                                                 (uint32_t)skip, in_place);
+                                                                 (uint32_t)skip, in_place, d_n);
     B200_LAUNCH_CHECK();
     B200_TRY(timer.mark());
     for (int pass = 0; pass < kRadixPasses; ++pass) {
         uint32_t *cur = status[pass & 1];
         uint32_t *next = (pass + 1 < kRadixPasses) ? status[(pass + 1) & 1] : nullptr;
-        B200_TRY(launch_onesweep(var, tiles, s, d_in, d_out, d_tmp, n, pass, ctl, cur, next, 1));
+        B200_TRY(launch_onesweep(var, tiles, s, d_in, d_out, d_tmp, n, pass, ctl, cur, next, d_n ? 3 : 1));
         B200_TRY(timer.mark());
     }
     if (skip) {
@@ -442,7 +443,7 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
         // once when it is not.  With skipping off the pass count is always even / lands in out.
         const size_t blocks = div_up(div_up(n, 4), 256);
         const unsigned grid = (unsigned)(blocks < (size_t)kNumSMs * 8 ? blocks : (size_t)kNumSMs * 8);
-        radix_final_copy_kernel<<<grid, 256, 0, s>>>(d_in, d_out, d_tmp, n, ctl);
+        radix_final_copy_kernel<<<grid, 256, 0, s>>>(d_in, d_out, d_tmp, n, ctl, d_n ? 1u : 0u);
         B200_LAUNCH_CHECK();
     }
     B200_TRY(timer.mark());
@@ -454,6 +455,12 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
 int radix_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, void *d_ws,
                size_t ws_bytes, cudaStream_t s) {
     return radix_sort_impl(d_in, d_out, d_tmp, n, d_ws, ws_bytes, s, nullptr);
+}
+
+int radix_sort_devn(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n_max, const uint32_t *d_n, void *d_ws,
+                    size_t ws_bytes, cudaStream_t s) {
+    if (d_n == nullptr) return B200SORT_ERR_INVALID;
+    return radix_sort_impl(d_in, d_out, d_tmp, n_max, d_ws, ws_bytes, s, nullptr, d_n);
 }
 
 // ---- sort-by-key ----------------------------------------------------------------

@@ -23,7 +23,8 @@ struct RadixControl {
     uint32_t final_copy;                       // 0 none, else copy from that kSel* buffer to out
     uint32_t hot[kRadixPasses];                // 0, or 1 + the most frequent digit value of the pass if it
                                                // holds > 1/8 of the keys
-    uint32_t pad1[3];
+    uint32_t n_dev;                            // number of keys, as the kernels use it (see radix_sort_devn)
+    uint32_t pad1[2];
 };
 constexpr uint32_t kSelIn = 1, kSelTmp = 2, kSelOut = 3;
 constexpr size_t kRadixZeroBytes    = offsetof(RadixControl, base);
@@ -46,6 +47,11 @@ int radix_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, vo
 // d_in == d_out and v_in == v_out (in place) or neither.
 int radix_sort_pairs(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const int32_t *v_in, int32_t *v_out,
                      int32_t *v_tmp, size_t n, void *d_ws, size_t ws_bytes, cudaStream_t s);
+// The same sort with the key count taken from DEVICE memory (*d_n <= n_max, read by the kernels when they run):
+// lets a caller whose n is produced by an earlier kernel (the multi-GPU exchange) enqueue the sort without a
+// host synchronisation.  Grids, workspace and status rows are sized for n_max.
+int radix_sort_devn(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n_max, const uint32_t *d_n, void *d_ws,
+                    size_t ws_bytes, cudaStream_t s);
 // Same, with CUDA events around every kernel: ms[0] histogram, ms[1..4] passes, ms[5] final copy.
 int radix_sort_timed(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, void *d_ws,
                      size_t ws_bytes, cudaStream_t s, float *ms);

@@ -52,8 +52,9 @@ __device__ __forceinline__ void hist_flush(uint32_t *sh, RadixControl *ctl, uint
 __global__ void __launch_bounds__(kHistThreads)
 radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl *ctl,
                        uint32_t *status_to_zero, size_t status_words, uint32_t skip_enabled,
-                       uint32_t in_place)
+                       uint32_t in_place, const uint32_t *d_n = nullptr)
 {
+    if (d_n != nullptr) n = *d_n;                       // key count produced on the device (<= the n the grid was sized for)
     extern __shared__ __align__(16) uint32_t sh[];
     __shared__ uint32_t s_warp_sums[kRadixBins / 32];
     __shared__ uint32_t s_skip[kRadixPasses];
@@ -147,6 +148,7 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
     //   out of place : writes alternate so that the LAST executed pass lands in out; the input
     //                  is never written.  No executed pass at all (all keys equal): copy in -> out.
     if (tid == 0) {
+        ctl->n_dev = (uint32_t)n;
         uint32_t executed = 0;
         for (int p = 0; p < kRadixPasses; ++p) executed += s_skip[p] ? 0u : 1u;
         uint32_t j = 0, cur = kSelIn;

@@ -8,8 +8,9 @@ namespace b200sort {
 // executed an odd number of passes, in -> out when an out-of-place sort executed none.
 __global__ void __launch_bounds__(256)
 radix_final_copy_kernel(const int32_t *in_buf, int32_t *out_buf, const int32_t *tmp_buf, size_t n,
-                        const RadixControl *ctl)
+                        const RadixControl *ctl, uint32_t n_from_ctl = 0)
 {
+    if (n_from_ctl) n = ctl->n_dev;
     const uint32_t sel = ctl->final_copy;
     if (sel == 0) return;
     const int32_t *src = (sel == kSelIn) ? in_buf : tmp_buf;

@@ -395,6 +395,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     uint32_t *s_misc   = s_g2 + kRadixBins;                   // [0..7] warp sums, [8..9] tickets
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (follow_plan & 2) n = ctl->n_dev;                      // key count produced on the device (radix_sort_devn)
     const size_t tiles = (n + kTile - 1) / kTile;
 
     const int32_t *in = in_buf;

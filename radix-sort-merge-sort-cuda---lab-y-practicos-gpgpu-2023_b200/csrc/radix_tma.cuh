@@ -161,6 +161,7 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
     uint32_t *s_misc   = s_win2 + kTmaWin2 * kRadixBins;         // [0..7] warp sums, [8] ticket, [10] tmem base, [16..17] mbarrier
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (follow_plan & 2) n = ctl->n_dev;                      // key count produced on the device (radix_sort_devn)
     const size_t tiles = (n + kTile - 1) / kTile;
 
     const int32_t *in = in_buf;
