@@ -33,6 +33,16 @@ build/obj/%.o: $(CSRC)/%.cu $(HDRS)
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o "$@" $(OBJS)
 
+# make checked -> <pkg>/libb200sort_checked.so: the same library with the kernels asserting their own bounds and
+# alignment invariants (csrc/common.cuh, B200_CHECK); B200SORT_LIB=libb200sort_checked.so makes the Python binding
+# load it (tools/sanitize.sh checked)
+COBJS := $(patsubst $(CSRC)/%.cu,build/obj_checked/%.o,$(SRCS))
+build/obj_checked/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build/obj_checked
+	$(NVCC) $(NVFLAGS) -DB200SORT_CHECKED -c "$<" -o "$@"
+checked: $(COBJS)
+	$(NVCC) $(ARCH) -shared -o "$(PKG)/libb200sort_checked.so" $(COBJS)
+
 oracle:
 	$(MAKE) -C oracle all
 	$(MAKE) -C oracle ref
@@ -54,6 +64,6 @@ ptxas:
 	@for f in $(SRCS); do echo "== $$f"; $(NVCC) $(NVFLAGS) -Xptxas -v -c "$$f" -o /dev/null 2>&1 | grep -E "Compiling|registers|spill" ; done
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(PKG)/libb200sort_checked.so
 
-.PHONY: all oracle drivers ptxas clean
+.PHONY: all oracle drivers ptxas clean checked

@@ -159,6 +159,12 @@ int         b200sort_radix_atomic_order_ok(void);
 /* Profiling aid: TIMING_* shapes stamp clock64() at their phase boundaries into this device buffer
  * (grid x 2 x 10 int64); NULL switches the probe off.  tools/phase_timing.py reads it. */
 int         b200sort_debug_set_phase_buffer(void *d_buf);
+/* Checked build (make CHECKED=1): the kernels assert their own bounds and alignment invariants (staged positions,
+ * destination indices, 16-byte alignment of every bulk copy) and count violations instead of touching the address.
+ * b200sort_debug_checked_build() is 1 for such a library; b200sort_debug_check_failures() BLOCKS and returns the
+ * violations counted so far on the current device (always 0 for the product build, which compiles the checks away). */
+int                b200sort_debug_checked_build(void);
+unsigned long long b200sort_debug_check_failures(void);
 /* Name of the shape that will actually be launched (after the self-test's verdict). */
 const char *b200sort_radix_effective_variant_name(void);
 /* Pass skipping: when a digit histogram shows one bin holding every key the pass is the

@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_NAME = "libb200sort.so"
+_LIB_NAME = os.environ.get("B200SORT_LIB", "libb200sort.so")     # libb200sort_checked.so: make checked
 
 ALGO_RADIX = 0
 ALGO_MERGE = 1
@@ -61,6 +61,8 @@ SIGNATURES = {
     "b200sort_radix_set_skip": (_i, [_i]),
     "b200sort_debug_set_phase_buffer": (_i, [_vp]),
     "b200sort_radix_atomic_order_ok": (_i, []),
+    "b200sort_debug_checked_build": (_i, []),
+    "b200sort_debug_check_failures": (_u64, []),
     "b200sort_radix_effective_variant_name": (ctypes.c_char_p, []),
     "b200sort_launch_count": (_u64, []),
     "b200sort_launch_count_reset": (None, []),

@@ -26,6 +26,8 @@ void radix_set_skip(int enabled);
 int radix_atomic_order_ok();
 int radix_set_phase_debug(long long *d_buf);
 const char *radix_effective_variant_name();
+unsigned long long radix_check_failures();
+unsigned long long dist_check_failures();
 
 namespace {
 
@@ -476,6 +478,14 @@ const char *b200sort_radix_variant_name(int variant) { return radix_variant_name
 size_t b200sort_radix_tile(void) { return radix_current_tile(); }
 int b200sort_debug_set_phase_buffer(void *d_buf) { return radix_set_phase_debug(static_cast<long long *>(d_buf)); }
 int b200sort_radix_atomic_order_ok(void) { return radix_atomic_order_ok(); }
+int b200sort_debug_checked_build(void) {
+#ifdef B200SORT_CHECKED
+    return 1;
+#else
+    return 0;
+#endif
+}
+unsigned long long b200sort_debug_check_failures(void) { return radix_check_failures() + dist_check_failures(); }
 const char *b200sort_radix_effective_variant_name(void) { return radix_effective_variant_name(); }
 int b200sort_radix_set_skip(int enabled) { radix_set_skip(enabled); return B200SORT_OK; }
 unsigned long long b200sort_launch_count(void) { return g_launch_count; }

@@ -45,6 +45,25 @@ inline int record_cuda(cudaError_t e) {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// ---- checked build (make CHECKED=1) ------------------------------------------------------------------
+// compute-sanitizer is closed on the pool this library is developed on (profiles/r02_sanitizer_closed_on_this_pool.txt),
+// so the bounds and alignment invariants of the kernels are asserted by the kernels themselves in a checked build:
+// a violated B200_CHECK counts into a per-translation-unit device counter instead of touching the address (the access
+// that follows is skipped by the caller where that is possible), and b200sort_debug_check_failures() adds them up.
+// tools/sanitize_target.py runs every kernel family under it; the product build compiles the checks away.
+#ifdef B200SORT_CHECKED
+static __device__ unsigned long long g_check_failures;
+#define B200_CHECK(cond) do { if (!(cond)) atomicAdd(&::b200sort::g_check_failures, 1ull); } while (0)
+static inline unsigned long long tu_check_failures() {
+    unsigned long long v = 0;
+    cudaMemcpyFromSymbol(&v, g_check_failures, sizeof v);
+    return v;
+}
+#else
+#define B200_CHECK(cond) do {} while (0)
+static inline unsigned long long tu_check_failures() { return 0; }
+#endif
+
 inline size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b) { return div_up(a, b) * b; }
 

@@ -53,6 +53,7 @@ struct Variant {
     int tile;
     size_t smem;
     OnesweepFn fn;
+    OnesweepFn fn_devn = nullptr;   // the same shape reading the key count from the control block (radix_sort_devn)
 };
 
 #define B200_VARIANT(W, I, B, M, C)                                                                 \
@@ -90,14 +91,16 @@ struct Variant {
 const Variant kVariants[] = {
     // ---- the shipped shapes ------------------------------------------------------------------------------------
     { "pipelined2_16w_ipt20_kRankAdd_pack1_late_ticket", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
-      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1> },   //  0: DEFAULT: persistent
+      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1>,
+      radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 0, 0, 1> },   //  0: DEFAULT: persistent
                                                //     CTAs, 10240-key tiles, delayed two-level look-back, 16-bit counters (two
                                                //     warps per row), ticket drawn after the look-back, write-out by the
                                                //     load/store pipe
     { "tma_16w_ipt20_kRankAdd_tmem_parked_bulk_store", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes,
       radix_onesweep_tma_kernel<0> },          //  1: keys parked in tensor memory, late co-aligned staging, TMA write-out
     { "pipelined2_16w_ipt20_kRankBallot_pack1_late_ticket", kRankBallot, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
-      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 1> },   //  2: the documented-
+      Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 1>,
+      radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 1, 0, 1> },   //  2: the documented-
                                                //     behaviour fallback: the default kernel ranked by ballots
     { "TIMING_tma_16w_ipt20", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes, radix_onesweep_tma_kernel<1> },   //  3
     { "TIMING_pipelined2_ipt20_pack", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
@@ -105,7 +108,16 @@ const Variant kVariants[] = {
     B200_PP2X_VARIANT(20, 0, 1),               //  5: variant 0 with the ticket drawn before the look-back (round 1's default)
     B200_VARIANT(16, 16, 2, kRankBallot, 1),   //  6: one tile per CTA, ballot-ranked (round 1's fallback)
 #ifdef B200SORT_EXPERIMENTS
-    // ---- every other shape measured in rounds 1-2 (profiles/r01_onesweep_variants.md): make EXPERIMENTS=1 ----------
+    // ---- every other shape measured in rounds 1-2 (profiles/r0*_onesweep_variants.md): make EXPERIMENTS=1 ----------
+    { "pipelined2_16w_ipt22_kRankAdd_pack1_late_ticket", kRankAdd, 0, 1, 512, Pipelined2Shape<22, 1>::kTile,
+      Pipelined2Shape<22, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<22, 0, 0, 1, 2, 0, 0, 1> },   //  7: 11264-key tiles
+    { "pipelined2_16w_ipt24_kRankAdd_pack1_late_ticket", kRankAdd, 0, 1, 512, Pipelined2Shape<24, 1>::kTile,
+      Pipelined2Shape<24, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<24, 0, 0, 1, 2, 0, 0, 1> },   //  8: 12288-key tiles
+    { "pipelined2_16w_ipt20_kRankAdd_pack1_late_ticket_prefetch", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1, 0, 1>::kTile,
+      Pipelined2Shape<20, 1, 0, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 0, 1> },   //  7: + the
+                                               //     previous tile's look-back rows fetched by bulk load under the ranking
+    { "TIMING_pipelined2_prefetch", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1, 0, 1>::kTile,
+      Pipelined2Shape<20, 1, 0, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 1, 0, 1, 2, 0, 0, 1, 0, 1> },   //  8
     B200_PP2X_VARIANT(20, 0, 1),               //  0: DEFAULT (fastest measured, 0.712 ms/pass): persistent CTAs,
                                                //     10240-key tiles, delayed two-level look-back, 16-bit counters
                                                //     (two warps per row)
@@ -249,11 +261,12 @@ size_t status_rows(const Variant &var, size_t tiles) {
 
 int launch_onesweep(const Variant &var, size_t tiles, cudaStream_t s, const int32_t *in, int32_t *out,
                     int32_t *tmp, size_t n, int pass, RadixControl *ctl, uint32_t *cur, uint32_t *next,
-                    int follow_plan) {
+                    int follow_plan, bool devn = false) {
+    if (devn && (var.fn_devn == nullptr || var.cluster != 0)) return B200SORT_ERR_INVALID;
     if (var.cluster <= 0) {          // persistent: one CTA per resident slot, tiles by ticket
         const unsigned slots = (var.cluster == 0 ? 2u : (unsigned)(-var.cluster)) * kNumSMs;
         const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
-        var.fn<<<grid, var.threads, var.smem, s>>>(in, out, tmp, n, pass, ctl, cur, next, follow_plan);
+        (devn ? var.fn_devn : var.fn)<<<grid, var.threads, var.smem, s>>>(in, out, tmp, n, pass, ctl, cur, next, follow_plan);
         B200_LAUNCH_CHECK();
         return B200SORT_OK;
     }
@@ -300,6 +313,7 @@ int radix_set_phase_debug(long long *d_buf) {
     return B200SORT_OK;
 }
 int radix_atomic_order_ok() { return atomic_order_ok(); }
+unsigned long long radix_check_failures() { return tu_check_failures(); }
 int radix_num_variants() { return kNumVariants; }
 const char *radix_variant_name(int v) { return (v >= 0 && v < kNumVariants) ? kVariants[v].name : nullptr; }
 int radix_set_variant(int v) {
@@ -412,8 +426,12 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
         B200_LAUNCH_CHECK();
         return B200SORT_OK;
     }
-    const int v = effective_variant();
+    int v = effective_variant();
+    if (d_n != nullptr && kVariants[v].fn_devn == nullptr) v = atomic_order_ok() ? 0 : kFallbackVariant;
     B200_TRY(ensure_smem_attr(v));
+    if (d_n != nullptr)
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(kVariants[v].fn_devn),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVariants[v].smem));
     B200_TRY(ensure_hist_attr());
     const Variant &var = kVariants[v];
     auto *ctl = static_cast<RadixControl *>(d_ws);
@@ -435,7 +453,7 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
     for (int pass = 0; pass < kRadixPasses; ++pass) {
         uint32_t *cur = status[pass & 1];
         uint32_t *next = (pass + 1 < kRadixPasses) ? status[(pass + 1) & 1] : nullptr;
-        B200_TRY(launch_onesweep(var, tiles, s, d_in, d_out, d_tmp, n, pass, ctl, cur, next, d_n ? 3 : 1));
+        B200_TRY(launch_onesweep(var, tiles, s, d_in, d_out, d_tmp, n, pass, ctl, cur, next, 1, d_n != nullptr));
         B200_TRY(timer.mark());
     }
     if (skip) {

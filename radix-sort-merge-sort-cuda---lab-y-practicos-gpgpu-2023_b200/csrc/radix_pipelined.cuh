@@ -1,6 +1,7 @@
 // radix_pipelined.cuh -- k2', k2'': the pass as a persistent, software-pipelined CTA (included by radix.cu).
 #pragma once
 #include "radix_tile.cuh"
+#include "radix_async.cuh"
 
 namespace b200sort {
 
@@ -350,7 +351,10 @@ radix_onesweep_pipelined_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t
 //        shared-memory traffic of the digit phase and of the zeroing.
 // KV   : every key carries a 32-bit value through the pass (sort-by-key): the
 //        values are loaded, staged and written beside the keys, so the staging area doubles.
-template <int IPT, int PACK = 0, int KV = 0>
+// PFW1 / PFW2: status rows of the previous tile's look-back that ONE thread fetches into shared memory with two bulk
+// loads (TMA) underneath the ranking: the nearest PFW1 tile rows of its group and the nearest PFW2 group rows.
+constexpr int kPfw1 = 12, kPfw2 = 6;                 // 18 KB: what is left of 2 x 113 KB per SM beside the 10240-key tile
+template <int IPT, int PACK = 0, int KV = 0, int PFW = 0>
 struct Pipelined2Shape {
     static constexpr int kThreads = 512;
     static constexpr int kTile = kThreads * IPT;
@@ -359,7 +363,8 @@ struct Pipelined2Shape {
         (size_t)kRows * kRadixBins * 4              // per-warp digit counters -> positions
         + (size_t)(KV ? 4 : 2) * kTile * 4          // two staging buffers (keys; KV: and two for the values)
         + (size_t)(2 + 1 + 2 + 1) * kRadixBins * 4  // gofs[2], total, tstart[2], previous tile's group prefix
-        + 128;
+        + 128
+        + (PFW ? (size_t)(kPfw1 + kPfw2) * kRadixBins * 4 : 0);
 };
 
 // EG   : the last tile of a group makes its GROUP row inclusive at once (it walks the earlier group rows
@@ -370,7 +375,10 @@ struct Pipelined2Shape {
 //        off, stages while they fly, then finishes the walk.  One CTA barrier before the write-out.
 // SAFE : rank with eight __ballot_sync per key and ONE atomic per distinct digit of the warp instruction (documented
 //        behaviour only) instead of one atomic per key (which needs same-address lanes to be resolved in lane order).
-template <int IPT, int TIMING, int SPLIT, int PACK, int KV, int EG = 0, int OVL = 0, int LATE = 0, int SAFE = 0>
+// DEVN : the key count is read from the control block (written by the histogram kernel from a device pointer,
+//        radix_sort_devn) instead of the kernel argument.  A separate instantiation: as a run-time switch it cost
+//        the default kernel 64 bytes of spills and 4 % (0.696 -> 0.726 ms per pass).
+template <int IPT, int TIMING, int SPLIT, int PACK, int KV, int EG = 0, int OVL = 0, int LATE = 0, int SAFE = 0, int PFW = 0, int DEVN = 0>
 __device__ __forceinline__ void
 radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
@@ -383,6 +391,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in pairs");
     static_assert(kTile + 64 < 65536, "PACK keeps 16-bit positions");
     static_assert(!(OVL && SPLIT), "OVL restructures the unsplit resolve");
+    static_assert(!PFW || (!SPLIT && !OVL && !EG), "the prefetched look-back is written for the unsplit resolve");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *s_table  = reinterpret_cast<uint32_t *>(smem_raw);                      // [kRows][256]
@@ -392,11 +401,21 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     uint32_t *s_total  = s_gofs + 2 * kRadixBins;                                     // [256]
     uint32_t *s_tstart = s_total + kRadixBins;                                        // [2][256]
     uint32_t *s_g2     = s_tstart + 2 * kRadixBins;           // [256] SPLIT: previous tile's prefix over earlier groups
-    uint32_t *s_misc   = s_g2 + kRadixBins;                   // [0..7] warp sums, [8..9] tickets
+    uint32_t *s_misc   = s_g2 + kRadixBins;                   // [0..7] warp sums, [8..9] tickets, [16..17] mbarrier
+    uint32_t *s_win1   = s_misc + 32;                         // PFW: [kPfw1][256] nearest tile rows, [kPfw2][256] group rows
+    uint32_t *s_win2   = s_win1 + kPfw1 * kRadixBins;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (follow_plan & 2) n = ctl->n_dev;                      // key count produced on the device (radix_sort_devn)
-    const size_t tiles = (n + kTile - 1) / kTile;
+    // The tile count (and, DEVN, the key count produced on the device: radix_sort_devn) lives in shared memory and is
+    // re-read where it is needed: held in registers it pushed the kernel over its 64 (16 to 64 bytes of spills).
+    if (tid == 0) {
+        const uint32_t n32 = DEVN ? ctl->n_dev : (uint32_t)n;
+        s_misc[20] = n32;
+        s_misc[21] = (uint32_t)(((size_t)n32 + kTile - 1) / kTile);
+    }
+    __syncthreads();
+    auto n_f = [&]() -> size_t { return DEVN ? (size_t)reinterpret_cast<volatile uint32_t *>(s_misc)[20] : n; };
+    auto tiles_f = [&]() -> size_t { return (size_t)reinterpret_cast<volatile uint32_t *>(s_misc)[21]; };
 
     const int32_t *in = in_buf;
     int32_t *out = out_buf;
@@ -404,7 +423,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     int32_t *vout = out_vals;
     if (follow_plan) {
         if (ctl->skip[pass]) {
-            const size_t rows = tiles + (tiles + kLookGroup - 1) / kLookGroup;
+            const size_t rows = tiles_f() + (tiles_f() + kLookGroup - 1) / kLookGroup;
             if (status_next != nullptr)
                 for (size_t row = blockIdx.x; row < rows; row += gridDim.x)
                     if (tid < kRadixBins) status_next[row * kRadixBins + tid] = 0;
@@ -444,7 +463,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     int32_t val[KV ? IPT : 1];
     auto load_tile = [&](uint32_t t) {
         const size_t tile_base = (size_t)t * kTile;
-        const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
+        const uint32_t valid = (n_f() - tile_base < (size_t)kTile) ? (uint32_t)(n_f() - tile_base) : (uint32_t)kTile;
         const int32_t *src = in + tile_base + wofs;
         if (valid == (uint32_t)kTile) {
 #pragma unroll
@@ -463,7 +482,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     };
     auto write_tile = [&](uint32_t t, int buf) {
         const size_t tile_base = (size_t)t * kTile;
-        const uint32_t valid = (n - tile_base < (size_t)kTile) ? (uint32_t)(n - tile_base) : (uint32_t)kTile;
+        const uint32_t valid = (n_f() - tile_base < (size_t)kTile) ? (uint32_t)(n_f() - tile_base) : (uint32_t)kTile;
         const int32_t *sk = s_keys + buf * kTile;
         const int32_t *sv = s_vals + buf * kTile;
         const uint32_t *go = s_gofs + buf * kRadixBins;
@@ -473,6 +492,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
                 const uint32_t p = tid + j * kThreads;
                 const int32_t k = sk[p];
                 const size_t dst = (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p);
+                B200_CHECK(dst < n_f());
                 st_stream(out + dst, k);
                 if (KV) st_stream(vout + dst, sv[p]);
             }
@@ -483,6 +503,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
                 if (p < valid) {
                     const int32_t k = sk[p];
                     const size_t dst = (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p);
+                    B200_CHECK(dst < n_f());
                     st_stream(out + dst, k);
                     if (KV) st_stream(vout + dst, sv[p]);
                 }
@@ -496,15 +517,32 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     bool p_in_known = false;
     uint32_t p_g = 0;                                         // EG: its prefix over the earlier groups, if known
     bool p_g_known = false;
+    // PFW: rows of the previous tile's look-back fetched by bulk load (issued when the iteration begins)
+    const uint32_t pf_mbar = smem_u32(&s_misc[16]);
+    uint32_t pf_have1 = 0, pf_have2 = 0, pf_parity = 0;
+    auto prefetch_rows = [&](uint32_t pt) {                   // every thread computes the counts, one thread issues
+        const uint32_t group = pt / kLookGroup, r = pt % kLookGroup;
+        const bool last_of_group = (r == kLookGroup - 1) || ((size_t)pt + 1 == tiles_f());
+        pf_have1 = last_of_group ? 0u : (r < (uint32_t)kPfw1 ? r : (uint32_t)kPfw1);
+        pf_have2 = group < (uint32_t)kPfw2 ? group : (uint32_t)kPfw2;
+        if (tid == kRadixBins && pf_have1 + pf_have2 > 0) {
+            fence_proxy_async_smem();
+            mbar_expect_tx(pf_mbar, (pf_have1 + pf_have2) * kRadixBins * 4);
+            if (pf_have1) bulk_load(smem_u32(s_win1), status_cur + ((size_t)pt - pf_have1) * kRadixBins, pf_have1 * kRadixBins * 4, pf_mbar);
+            if (pf_have2) bulk_load(smem_u32(s_win2), status_cur + (tiles_f() + group - pf_have2) * kRadixBins, pf_have2 * kRadixBins * 4, pf_mbar);
+        }
+    };
     // !SPLIT: the previous tile's look-back, run by group B alone: fills s_gofs[buf].
     auto resolve_prev = [&](uint32_t pt, int buf) {
         const uint32_t group = pt / kLookGroup, r = pt % kLookGroup;
-        const bool last_of_group = (r == kLookGroup - 1) || ((size_t)pt + 1 == tiles);
+        const bool last_of_group = (r == kLookGroup - 1) || ((size_t)pt + 1 == tiles_f());
         uint32_t *row = status_cur + (size_t)pt * kRadixBins + bd;
-        uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
+        uint32_t *grow = status_cur + (tiles_f() + group) * kRadixBins + bd;
+        if (PFW && pf_have1 + pf_have2 > 0) { mbar_wait(pf_mbar, pf_parity); pf_parity ^= 1; }   // the fetched rows have landed
         uint32_t inprev = p_in;
         if (!p_in_known) {
-            inprev = (r > 0) ? walk_back<W>(row - kRadixBins, r) : 0u;
+            inprev = (r > 0) ? (PFW ? walk_back_prefetched<W>(s_win1 + bd, pf_have1, row - kRadixBins, r)
+                                    : walk_back<W>(row - kRadixBins, r)) : 0u;
             if (r > 0) st_relaxed_gpu(row, kFlagIncl | (inprev + p_total));   // shortens later walks
         }
         uint32_t gprev = 0;
@@ -512,10 +550,12 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
             if (EG && p_g_known) {
                 gprev = p_g;                                  // summed (and published) when the tile was published
             } else {
-                gprev = walk_back<W>(grow - kRadixBins, group);
+                gprev = PFW ? walk_back_prefetched<W>(s_win2 + bd, pf_have2, grow - kRadixBins, group)
+                            : walk_back<W>(grow - kRadixBins, group);
                 if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + inprev + p_total) & kValueMask));
             }
         }
+        B200_CHECK((size_t)digit_base + inprev + gprev + p_total <= n_f());     // the run lies inside the array
         s_gofs[buf * kRadixBins + bd] = digit_base + inprev + gprev - s_tstart[buf * kRadixBins + bd];
     };
     // SPLIT: the two walks are given to the two groups and started before anything else in the digit
@@ -529,14 +569,14 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     uint32_t win2[W2];
     auto level2_load = [&](uint32_t pt, uint32_t dg) {
         const uint32_t group = pt / kLookGroup;
-        const uint32_t *first = status_cur + (tiles + group) * kRadixBins + dg - kRadixBins;
+        const uint32_t *first = status_cur + (tiles_f() + group) * kRadixBins + dg - kRadixBins;
 #pragma unroll
         for (int j = 0; j < W2; ++j)
             win2[j] = ((uint32_t)(j + 1) <= group) ? ld_relaxed_gpu(first - (size_t)j * kRadixBins) : kFlagIncl;
     };
     auto level2_finish = [&](uint32_t pt, uint32_t dg) -> uint32_t {
         const uint32_t group = pt / kLookGroup;
-        const uint32_t *first = status_cur + (tiles + group) * kRadixBins + dg - kRadixBins;
+        const uint32_t *first = status_cur + (tiles_f() + group) * kRadixBins + dg - kRadixBins;
         uint32_t acc = 0, back = 1;
         bool have = true;
         for (;;) {
@@ -570,26 +610,30 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
     };
     auto combine_prev = [&](uint32_t pt, int buf, uint32_t q_total, uint32_t q_in) {   // group B, after A's level2_finish
         const uint32_t group = pt / kLookGroup;
-        const bool last = (pt % kLookGroup == kLookGroup - 1) || ((size_t)pt + 1 == tiles);
+        const bool last = (pt % kLookGroup == kLookGroup - 1) || ((size_t)pt + 1 == tiles_f());
         const uint32_t gprev = s_g2[bd];
         if (last && group > 0)
-            st_relaxed_gpu(status_cur + (tiles + group) * kRadixBins + bd, kFlagIncl | ((gprev + q_in + q_total) & kValueMask));
+            st_relaxed_gpu(status_cur + (tiles_f() + group) * kRadixBins + bd, kFlagIncl | ((gprev + q_in + q_total) & kValueMask));
         s_gofs[buf * kRadixBins + bd] = digit_base + q_in + gprev - s_tstart[buf * kRadixBins + bd];
     };
 
     zero_counters();
-    if (tid == 0) s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
+    if (tid == 0) {
+        s_misc[8] = atomicAdd(&ctl->ticket[pass], 1u);
+        if (PFW) { mbar_init(pf_mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    }
     __syncthreads();
     uint32_t tile = s_misc[8];
     uint32_t prev_tile = 0xFFFFFFFFu;
-    if (tile < tiles) load_tile(tile);
+    if (tile < tiles_f()) load_tile(tile);
     int b = 0;
     uint32_t iter = 0;
 
-    while (tile < tiles) {
+    while (tile < tiles_f()) {
         const uint32_t dbg_tile = tile;
         if (TIMING) { asm volatile("" :: "r"(key[0]), "r"(key[IPT - 1])); }
         B200_STAMP(0);                                        // this tile's keys are in registers
+        if (PFW) { pf_have1 = pf_have2 = 0; if (prev_tile != 0xFFFFFFFFu) prefetch_rows(prev_tile); }
         if (PACK) pair_bar();                                 // my partner has cleared its half of our counter row
         // ---- rank: one shared-memory atomicAdd per key (lane-ordered; see the self-test) ----------
         uint32_t rank2[IPT / 2];
@@ -708,12 +752,12 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
             bar_sync(2, 512);
             const uint32_t total = s_total[bd];
             const uint32_t group = tile / kLookGroup, r = tile % kLookGroup;
-            const bool last_of_group = (r == kLookGroup - 1) || ((size_t)tile + 1 == tiles);
+            const bool last_of_group = (r == kLookGroup - 1) || ((size_t)tile + 1 == tiles_f());
             uint32_t *row = status_cur + (size_t)tile * kRadixBins + bd;
             st_relaxed_gpu(row, (r == 0 ? kFlagIncl : kFlagLocal) | total);
             if (status_next != nullptr) {
                 status_next[(size_t)tile * kRadixBins + bd] = 0;
-                if (last_of_group) status_next[(tiles + group) * kRadixBins + bd] = 0;
+                if (last_of_group) status_next[(tiles_f() + group) * kRadixBins + bd] = 0;
             }
             B200_STAMP(10);                                   // published
             if (!SPLIT && !OVL) {
@@ -739,7 +783,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
                 p_in = (r > 0) ? walk_back<W>(row - kRadixBins, r) : 0u;
                 p_in_known = true;
                 if (r > 0) st_relaxed_gpu(row, kFlagIncl | (p_in + total));
-                uint32_t *grow = status_cur + (tiles + group) * kRadixBins + bd;
+                uint32_t *grow = status_cur + (tiles_f() + group) * kRadixBins + bd;
                 st_relaxed_gpu(grow, (group == 0 ? kFlagIncl : kFlagLocal) | (p_in + total));
                 if (EG && !SPLIT && group > 0) {
                     // every row this walk waits for is published by a running CTA before that CTA waits for
@@ -751,7 +795,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
             }
             __syncwarp();
             // LATE: the next tile's ticket is drawn AFTER the look-back (the one phase whose length varies), so that
-            // from ticket to publication every tile takes the same time and tiles are published in ticket order
+            // from ticket to publication every tile takes the same time and tiles_f() are published in ticket order
             if (LATE && tid == kRadixBins) s_misc[8 + ((iter + 1) & 1)] = atomicAdd(&ctl->ticket[pass], 1u);
             if (OVL) bar_sync(11, 512);                       // group A's positions are final
             B200_STAMP(3);                                    // group B done
@@ -769,6 +813,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
             for (int i = 0; i < IPT; ++i) {
                 const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
                 const uint32_t pos = my_half(wt[digit_of(key[i], shift, flip)]) + r;
+                B200_CHECK(pos < (uint32_t)kTile);
                 sk[pos] = key[i];
                 if (KV) sv[pos] = val[KV ? i : 0];
             }
@@ -778,7 +823,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
         if (!(PACK && SPLIT)) { zero_counters(); __syncwarp(); }
         B200_STAMP(5);                                        // staged
         // ---- the next tile's loads go out now and land while the previous tile is written --------
-        if (next < tiles) load_tile(next);
+        if (next < tiles_f()) load_tile(next);
         B200_STAMP(6);
         if (SPLIT) {
             __syncthreads();                                  // SYNC3: the previous tile's offsets are in s_gofs
@@ -787,13 +832,13 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
         if (OVL) {
             if (in_b && have_prev) {                          // finish the previous tile's walk over the group rows
                 const uint32_t pg = prev_tile / kLookGroup;
-                const bool plast = (prev_tile % kLookGroup == kLookGroup - 1) || ((size_t)prev_tile + 1 == tiles);
+                const bool plast = (prev_tile % kLookGroup == kLookGroup - 1) || ((size_t)prev_tile + 1 == tiles_f());
                 uint32_t gprev = 0;
                 if (pg > 0) {
                     if (o_g_known) gprev = o_g;
                     else {
                         gprev = level2_finish(prev_tile, bd);
-                        if (plast) st_relaxed_gpu(status_cur + (tiles + pg) * kRadixBins + bd,
+                        if (plast) st_relaxed_gpu(status_cur + (tiles_f() + pg) * kRadixBins + bd,
                                                   kFlagIncl | ((gprev + o_in + o_total) & kValueMask));
                     }
                 }
@@ -820,6 +865,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
             __syncthreads();
             if (in_b) combine_prev(prev_tile, b ^ 1, p_total, q_in);
         } else {
+            if (PFW) pf_have1 = pf_have2 = 0;                 // nothing was fetched for the last tile
             if (in_b) resolve_prev(prev_tile, b ^ 1);
         }
         __syncthreads();
@@ -828,13 +874,13 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
 }
 
 // MINB: CTAs per SM the register allocation is held to (3 with tiles of <= 6144 keys: 40 registers).
-template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0, int MINB = 2, int EG = 0, int OVL = 0, int LATE = 0, int SAFE = 0>
+template <int IPT, int TIMING = 0, int SPLIT = 0, int PACK = 0, int MINB = 2, int EG = 0, int OVL = 0, int LATE = 0, int SAFE = 0, int PFW = 0, int DEVN = 0>
 __global__ void __launch_bounds__(512, MINB)
 radix_onesweep_pipelined2_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n,
                                  int pass, RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
                                  int follow_plan)
 {
-    radix_onesweep_pipelined2_body<IPT, TIMING, SPLIT, PACK, 0, EG, OVL, LATE, SAFE>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
+    radix_onesweep_pipelined2_body<IPT, TIMING, SPLIT, PACK, 0, EG, OVL, LATE, SAFE, PFW, DEVN>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur,
                                                                 status_next, follow_plan, nullptr, nullptr, nullptr);
 }
 

@@ -109,7 +109,6 @@ radix_onesweep_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf,
                       RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next,
                       int follow_plan)
 {
-    if (follow_plan & 2) n = ctl->n_dev;                      // key count produced on the device (radix_sort_devn)
     using Shape = OnesweepShape<WARPS, IPT, MODE>;
     constexpr int kThreads = Shape::kThreads;
     constexpr int kTile    = Shape::kTile;

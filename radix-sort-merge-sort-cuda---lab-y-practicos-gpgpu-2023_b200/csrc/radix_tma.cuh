@@ -41,8 +41,6 @@
 
 namespace b200sort {
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 // ---- tensor memory: lane-private parking for registers ---------------------------------------------------
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
@@ -66,56 +64,6 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&r)[2]) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// ---- 1-D bulk copies (TMA) ------------------------------------------------------------------------------------
-__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t mbar) {
-    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
-                 :: "r"(mbar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(const uint32_t *p) { return *reinterpret_cast<const uint4 *>(p); }
-__device__ __forceinline__ void sts128(uint32_t *p, uint4 v) { *reinterpret_cast<uint4 *>(p) = v; }
-
-// Walk back over status rows like walk_back, the nearest `have` of them already sitting in shared memory in
-// memory order (win[(have - d) * 256] = the row at distance d, for my digit); eight loads in flight.  A word
-// that was not published yet when it was fetched is polled in global memory.
-template <int W>
-__device__ __forceinline__ uint32_t walk_back_prefetched(const uint32_t *win, uint32_t have, const uint32_t *first,
-                                                         uint32_t max_dist) {
-    uint32_t acc = 0;
-    for (uint32_t base = 0; base < have; base += 8) {
-        uint32_t w[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = (base + j < have) ? win[(have - 1 - base - j) * kRadixBins] : 0u;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (base + j < have) {
-                uint32_t x = w[j];
-                while ((x & ~kValueMask) == 0) x = ld_relaxed_gpu(first - (size_t)(base + j) * kRadixBins);
-                acc += x & kValueMask;
-                if ((x & ~kValueMask) == kFlagIncl) return acc;
-            }
-        }
-    }
-    if (max_dist > have) acc += walk_back<W>(first - (size_t)have * kRadixBins, max_dist - have);
-    return acc;
-}
 
 constexpr int kTmaIpt = 20;
 constexpr int kTmaThreads = 512;
@@ -161,7 +109,6 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
     uint32_t *s_misc   = s_win2 + kTmaWin2 * kRadixBins;         // [0..7] warp sums, [8] ticket, [10] tmem base, [16..17] mbarrier
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (follow_plan & 2) n = ctl->n_dev;                      // key count produced on the device (radix_sort_devn)
     const size_t tiles = (n + kTile - 1) / kTile;
 
     const int32_t *in = in_buf;
@@ -412,6 +359,7 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
                     if (i < count) {
                         const uint32_t r = (i & 1) ? (rk[i / 2] >> 16) : (rk[i / 2] & 0xffffu);
                         const uint32_t pos = ((wt[digit_of((int32_t)k[i], shift, flip)] >> sh) & 0xffffu) + r;
+                        B200_CHECK(pos < (uint32_t)kTmaStageWords);
                         s_stage[pos] = (int32_t)k[i];
                     }
                 }
@@ -452,6 +400,8 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
                 uint32_t head = (4u - (g & 3u)) & 3u;
                 if (head > c) head = c;
                 const uint32_t body = (c - head) & ~3u;
+                B200_CHECK(((g + head) & 3u) == 0 && ((start + head) & 3u) == 0);          // 16-byte aligned on both sides
+                B200_CHECK((size_t)g - gmis + c <= n && start + c <= (uint32_t)kTmaStageWords); // inside the array and the tile
                 if (body > 0) bulk_store(out_al + g + head, stage_s + (start + head) * 4u, body * 4u);
                 bulk_commit();
             }
@@ -467,6 +417,7 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
                 const uint32_t tail = c - head - body;
                 const uint32_t idx = (sl < 3u) ? sl : head + body + (sl - 3u);
                 const bool on = (sl < 3u) ? (sl < head) : (sl - 3u < tail);
+                B200_CHECK(!on || ((size_t)g - gmis + idx < n && start + idx < (uint32_t)kTmaStageWords));
                 if (on) st_stream(out_al + g + idx, s_stage[start + idx]);
             }
         }

@@ -2,7 +2,7 @@
 """Condense an .ncu-rep (read here, no GPU needed) into the few numbers the roofline argument uses.
 
     python tools/ncu_summary.py gpurun_out/onesweep_v0.ncu-rep [more.ncu-rep ...] > profiles/rNN_x.md
-Also prints a JSON object per kernel (--json FILE appends to a dict keyed by kernel name)."""
+Also writes the items as JSON (--json FILE; --variant NAME stamps the shape the capture was taken on)."""
 import csv
 import io
 import json
@@ -70,9 +70,16 @@ def main():
         i = args.index("--json")
         json_out = args[i + 1]
         del args[i:i + 2]
+    variant = None          # --variant NAME: the compiled shape the capture was taken on (bench.py checks it)
+    if "--variant" in args:
+        i = args.index("--variant")
+        variant = args[i + 1]
+        del args[i:i + 2]
     allitems = []
     for p in args:
         for item in summarize(p):
+            if variant is not None:
+                item["variant"] = variant
             allitems.append(item)
             print(f"### {item['kernel'][:120]}\n\nsource: `{item['file']}`\n")
             print("| metric | value |\n|---|---|")

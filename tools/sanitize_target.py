@@ -86,4 +86,16 @@ h = datagen.lab_rand(4096, 100, seed=1)
 wh = oracle.order_array(h)
 a = h.copy(); check(L.b200sort_order_array_host(a.ctypes.data, a.size, ALGO_RADIX)); same(a, wh, "order_array host operator")
 L.b200sort_host_release()
+if L.b200sort_debug_checked_build():
+    # full-size runs too: the checks cost little
+    for dist_name in ("uniform", "skewed90", "ascending"):
+        k = datagen.make(dist_name, (1 << 24) + 4321, 8)
+        same(gpu_sort(k, ALGO_RADIX), oracle.radix_sort(k), f"radix default n=2^24+4321 {dist_name}")
+    check(L.b200sort_radix_set_variant(1))
+    k = datagen.uniform((1 << 24) + 4321, 9)
+    same(gpu_sort(k, ALGO_RADIX), oracle.radix_sort(k), "radix TMA shape n=2^24+4321 uniform")
+    check(L.b200sort_radix_set_variant(0))
+    fails = int(L.b200sort_debug_check_failures())
+    print(f"CHECKED BUILD: {fails} violated kernel invariants (staged positions, destination indices, bulk-copy alignment)", flush=True)
+    assert fails == 0
 print("SANITIZE TARGET PASSED", flush=True)
