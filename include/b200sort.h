@@ -165,6 +165,8 @@ int         b200sort_debug_set_phase_buffer(void *d_buf);
  * violations counted so far on the current device (always 0 for the product build, which compiles the checks away). */
 int                b200sort_debug_checked_build(void);
 unsigned long long b200sort_debug_check_failures(void);
+/* The same per check site (csrc: B200_CHECK_AT(site, ...)); per_site[16] is overwritten. */
+unsigned long long b200sort_debug_check_failures_by_site(unsigned long long *per_site);
 /* Name of the shape that will actually be launched (after the self-test's verdict). */
 const char *b200sort_radix_effective_variant_name(void);
 /* Pass skipping: when a digit histogram shows one bin holding every key the pass is the

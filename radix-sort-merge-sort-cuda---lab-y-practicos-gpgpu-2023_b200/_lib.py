@@ -63,6 +63,7 @@ SIGNATURES = {
     "b200sort_radix_atomic_order_ok": (_i, []),
     "b200sort_debug_checked_build": (_i, []),
     "b200sort_debug_check_failures": (_u64, []),
+    "b200sort_debug_check_failures_by_site": (_u64, [_vp]),
     "b200sort_radix_effective_variant_name": (ctypes.c_char_p, []),
     "b200sort_launch_count": (_u64, []),
     "b200sort_launch_count_reset": (None, []),

@@ -26,8 +26,8 @@ void radix_set_skip(int enabled);
 int radix_atomic_order_ok();
 int radix_set_phase_debug(long long *d_buf);
 const char *radix_effective_variant_name();
-unsigned long long radix_check_failures();
-unsigned long long dist_check_failures();
+unsigned long long radix_check_failures(unsigned long long *per_site);
+unsigned long long dist_check_failures(unsigned long long *per_site);
 
 namespace {
 
@@ -485,7 +485,12 @@ int b200sort_debug_checked_build(void) {
     return 0;
 #endif
 }
-unsigned long long b200sort_debug_check_failures(void) { return radix_check_failures() + dist_check_failures(); }
+unsigned long long b200sort_debug_check_failures(void) { return radix_check_failures(nullptr) + dist_check_failures(nullptr); }
+unsigned long long b200sort_debug_check_failures_by_site(unsigned long long *per_site /* [16], overwritten */) {
+    if (per_site == nullptr) return 0;
+    for (int i = 0; i < 16; ++i) per_site[i] = 0;
+    return radix_check_failures(per_site) + dist_check_failures(per_site);
+}
 const char *b200sort_radix_effective_variant_name(void) { return radix_effective_variant_name(); }
 int b200sort_radix_set_skip(int enabled) { radix_set_skip(enabled); return B200SORT_OK; }
 unsigned long long b200sort_launch_count(void) { return g_launch_count; }

@@ -52,16 +52,19 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // that follows is skipped by the caller where that is possible), and b200sort_debug_check_failures() adds them up.
 // tools/sanitize_target.py runs every kernel family under it; the product build compiles the checks away.
 #ifdef B200SORT_CHECKED
-static __device__ unsigned long long g_check_failures;
-#define B200_CHECK(cond) do { if (!(cond)) atomicAdd(&::b200sort::g_check_failures, 1ull); } while (0)
-static inline unsigned long long tu_check_failures() {
-    unsigned long long v = 0;
-    cudaMemcpyFromSymbol(&v, g_check_failures, sizeof v);
-    return v;
+static __device__ unsigned long long g_check_failures[16];      // one counter per check site (B200_CHECK_AT)
+#define B200_CHECK_AT(site, cond) do { if (!(cond)) atomicAdd(&::b200sort::g_check_failures[site], 1ull); } while (0)
+#define B200_CHECK(cond) B200_CHECK_AT(0, cond)
+static inline unsigned long long tu_check_failures(unsigned long long *per_site = nullptr) {
+    unsigned long long v[16] = {0}, sum = 0;
+    cudaMemcpyFromSymbol(v, g_check_failures, sizeof v);
+    for (int i = 0; i < 16; ++i) { sum += v[i]; if (per_site) per_site[i] += v[i]; }
+    return sum;
 }
 #else
+#define B200_CHECK_AT(site, cond) do {} while (0)
 #define B200_CHECK(cond) do {} while (0)
-static inline unsigned long long tu_check_failures() { return 0; }
+static inline unsigned long long tu_check_failures(unsigned long long * = nullptr) { return 0; }
 #endif
 
 inline size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }

@@ -159,7 +159,7 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
             if (p < valid) {
                 const uint32_t d = slot[i] >> 16;
                 const uint32_t q = s_start[d] + (slot[i] & 0xffffu);
-                B200_CHECK(q < (uint32_t)kSlots && d < (uint32_t)world);
+                B200_CHECK_AT(9, q < (uint32_t)kSlots && d < (uint32_t)world);
                 s_keys[q] = key[i];
                 if (!TMA) s_dest[q] = (uint8_t)d;
             }
@@ -173,7 +173,7 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
                 uint32_t head = (4u - ((uint32_t)s_gbase[tid] & 3u)) & 3u;
                 if (head > c) head = c;
                 const uint32_t body = (c - head) & ~3u;
-                B200_CHECK(((start + head) & 3u) == 0 && ((s_gbase[tid] + head) & 3ull) == 0);   // 16-byte aligned on both sides
+                B200_CHECK_AT(10, body == 0 || (((start + head) & 3u) == 0 && ((s_gbase[tid] + head) & 3ull) == 0));   // 16-byte aligned on both sides
                 if (body > 0)
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  :: "l"(dst + head), "r"((uint32_t)__cvta_generic_to_shared(s_keys + start + head)), "r"(body * 4u) : "memory");
@@ -293,7 +293,7 @@ dist_plan_kernel(const unsigned long long *__restrict__ all_hist, uint32_t world
 
 // ================================================================================================
 // the destination cursors, then (device planner) the prefix sums of the global bin counts
-unsigned long long dist_check_failures() { return tu_check_failures(); }
+unsigned long long dist_check_failures(unsigned long long *per_site) { return tu_check_failures(per_site); }
 size_t dist_workspace_bytes(size_t, int bits) { return 256 + (((size_t)1 << bits) + 1) * sizeof(unsigned long long); }
 
 static size_t partition_smem(int bits, int threads) {

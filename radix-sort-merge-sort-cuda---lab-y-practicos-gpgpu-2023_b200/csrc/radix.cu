@@ -313,7 +313,7 @@ int radix_set_phase_debug(long long *d_buf) {
     return B200SORT_OK;
 }
 int radix_atomic_order_ok() { return atomic_order_ok(); }
-unsigned long long radix_check_failures() { return tu_check_failures(); }
+unsigned long long radix_check_failures(unsigned long long *per_site) { return tu_check_failures(per_site); }
 int radix_num_variants() { return kNumVariants; }
 const char *radix_variant_name(int v) { return (v >= 0 && v < kNumVariants) ? kVariants[v].name : nullptr; }
 int radix_set_variant(int v) {

@@ -492,7 +492,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
                 const uint32_t p = tid + j * kThreads;
                 const int32_t k = sk[p];
                 const size_t dst = (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p);
-                B200_CHECK(dst < n_f());
+                B200_CHECK_AT(2, dst < n_f());
                 st_stream(out + dst, k);
                 if (KV) st_stream(vout + dst, sv[p]);
             }
@@ -503,7 +503,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
                 if (p < valid) {
                     const int32_t k = sk[p];
                     const size_t dst = (size_t)(uint32_t)(go[digit_of(k, shift, flip)] + p);
-                    B200_CHECK(dst < n_f());
+                    B200_CHECK_AT(2, dst < n_f());
                     st_stream(out + dst, k);
                     if (KV) st_stream(vout + dst, sv[p]);
                 }
@@ -555,7 +555,8 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
                 if (last_of_group) st_relaxed_gpu(grow, kFlagIncl | ((gprev + inprev + p_total) & kValueMask));
             }
         }
-        B200_CHECK((size_t)digit_base + inprev + gprev + p_total <= n_f());     // the run lies inside the array
+        // the run lies inside the array (the last tile's count of digit 255 includes its INT_MAX padding slots)
+        B200_CHECK_AT(3, (size_t)digit_base + inprev + gprev + (((size_t)pt + 1 == tiles_f()) ? 0u : p_total) <= n_f());
         s_gofs[buf * kRadixBins + bd] = digit_base + inprev + gprev - s_tstart[buf * kRadixBins + bd];
     };
     // SPLIT: the two walks are given to the two groups and started before anything else in the digit
@@ -813,7 +814,7 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
             for (int i = 0; i < IPT; ++i) {
                 const uint32_t r = (i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu);
                 const uint32_t pos = my_half(wt[digit_of(key[i], shift, flip)]) + r;
-                B200_CHECK(pos < (uint32_t)kTile);
+                B200_CHECK_AT(1, pos < (uint32_t)kTile);
                 sk[pos] = key[i];
                 if (KV) sv[pos] = val[KV ? i : 0];
             }

@@ -75,7 +75,7 @@ radix_small_kernel(const int32_t *in, int32_t *out, uint32_t n)
         __syncthreads();                                      // positions final
 #pragma unroll
         for (int i = 0; i < kSmallIpt; ++i) {
-            B200_CHECK(wt[digit_of(key[i], shift, flip)] + rank[i] < (uint32_t)kSmallTile);
+            B200_CHECK_AT(8, wt[digit_of(key[i], shift, flip)] + rank[i] < (uint32_t)kSmallTile);
             dst[wt[digit_of(key[i], shift, flip)] + rank[i]] = key[i];
         }
         __syncthreads();                                      // dst complete; the counters may be cleared

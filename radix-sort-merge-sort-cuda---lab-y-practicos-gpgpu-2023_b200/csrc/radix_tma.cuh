@@ -359,7 +359,7 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
                     if (i < count) {
                         const uint32_t r = (i & 1) ? (rk[i / 2] >> 16) : (rk[i / 2] & 0xffffu);
                         const uint32_t pos = ((wt[digit_of((int32_t)k[i], shift, flip)] >> sh) & 0xffffu) + r;
-                        B200_CHECK(pos < (uint32_t)kTmaStageWords);
+                        B200_CHECK_AT(4, pos < (uint32_t)kTmaStageWords);
                         s_stage[pos] = (int32_t)k[i];
                     }
                 }
@@ -400,8 +400,8 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
                 uint32_t head = (4u - (g & 3u)) & 3u;
                 if (head > c) head = c;
                 const uint32_t body = (c - head) & ~3u;
-                B200_CHECK(((g + head) & 3u) == 0 && ((start + head) & 3u) == 0);          // 16-byte aligned on both sides
-                B200_CHECK((size_t)g - gmis + c <= n && start + c <= (uint32_t)kTmaStageWords); // inside the array and the tile
+                B200_CHECK_AT(5, body == 0 || (((g + head) & 3u) == 0 && ((start + head) & 3u) == 0));          // 16-byte aligned on both sides
+                B200_CHECK_AT(6, (size_t)g - gmis + c <= n && start + c <= (uint32_t)kTmaStageWords); // inside the array and the tile
                 if (body > 0) bulk_store(out_al + g + head, stage_s + (start + head) * 4u, body * 4u);
                 bulk_commit();
             }
@@ -417,7 +417,7 @@ radix_onesweep_tma_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_
                 const uint32_t tail = c - head - body;
                 const uint32_t idx = (sl < 3u) ? sl : head + body + (sl - 3u);
                 const bool on = (sl < 3u) ? (sl < head) : (sl - 3u < tail);
-                B200_CHECK(!on || ((size_t)g - gmis + idx < n && start + idx < (uint32_t)kTmaStageWords));
+                B200_CHECK_AT(7, !on || ((size_t)g - gmis + idx < n && start + idx < (uint32_t)kTmaStageWords));
                 if (on) st_stream(out_al + g + idx, s_stage[start + idx]);
             }
         }

@@ -95,7 +95,9 @@ if L.b200sort_debug_checked_build():
     k = datagen.uniform((1 << 24) + 4321, 9)
     same(gpu_sort(k, ALGO_RADIX), oracle.radix_sort(k), "radix TMA shape n=2^24+4321 uniform")
     check(L.b200sort_radix_set_variant(0))
-    fails = int(L.b200sort_debug_check_failures())
+    sites = (ctypes.c_ulonglong * 16)()
+    fails = int(L.b200sort_debug_check_failures_by_site(ctypes.cast(sites, ctypes.c_void_p)))
+    print('per check site:', list(sites), flush=True)
     print(f"CHECKED BUILD: {fails} violated kernel invariants (staged positions, destination indices, bulk-copy alignment)", flush=True)
     assert fails == 0
 print("SANITIZE TARGET PASSED", flush=True)
