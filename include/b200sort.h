@@ -239,16 +239,21 @@ int b200sort_dist_partition_i32(const int32_t *d_keys, size_t n, int bits, int w
  * keys (then the partition kernel writes nothing).  Same boundaries as b200sort_dist_plan, bit for bit.
  * b200sort_dist_partition_planned_i32 takes its offsets from that record, and b200sort_radix_copy_devn_i32 sorts
  * what arrived with the key count read from device memory (d_n = the record's m; n_max sizes grids and workspace),
- * so a whole distributed sort is enqueued without the host ever reading a count. */
+ * so a whole distributed sort is enqueued without the host ever reading a count.
+ * d_src_hist (may be NULL; uint32[world][4][256], overwritten): the partition kernel also counts, per destination,
+ * the four 8-bit digit histograms of the keys it sends there (of key ^ 0x80000000, as b200sort_radix_histogram_i32).
+ * Summed over the source ranks (a reduce-scatter, which doubles as the barrier after the exchange) row r is the
+ * histogram of exactly what rank r received; passed as d_hist (may be NULL) to b200sort_radix_copy_devn_i32 it lets
+ * the local sort skip its own histogram kernel. */
 #define B200SORT_DIST_PLAN_BYTES 400
 int b200sort_dist_plan_device(const unsigned long long *d_all_hist, int world, int rank, int bits,
                               unsigned long long cap, int *d_bin_owner, void *d_plan,
                               void *d_ws, size_t ws_bytes, void *stream);
 int b200sort_dist_partition_planned_i32(const int32_t *d_keys, size_t n, int bits, int world,
                                         int32_t *const *h_dst_base, const int *d_bin_owner, const void *d_plan,
-                                        void *d_ws, size_t ws_bytes, void *stream);
+                                        unsigned int *d_src_hist, void *d_ws, size_t ws_bytes, void *stream);
 int b200sort_radix_copy_devn_i32(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n_max,
-                                 const uint32_t *d_n, void *d_ws, size_t ws_bytes, void *stream);
+                                 const uint32_t *d_n, const uint32_t *d_hist, void *d_ws, size_t ws_bytes, void *stream);
 /* Plain cudaMalloc / cudaFree (receive buffers must be whole allocations to be exported) and the
  * CUDA IPC plumbing that lets ranks (separate processes) map each other's receive buffers. */
 #define B200SORT_IPC_HANDLE_BYTES 64

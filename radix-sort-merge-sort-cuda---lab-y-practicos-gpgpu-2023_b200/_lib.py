@@ -72,8 +72,8 @@ SIGNATURES = {
     "b200sort_dist_workspace_bytes": (_sz, [_sz, _i]),
     "b200sort_dist_partition_i32": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200sort_dist_plan_device": (_i, [_vp, _i, _i, _i, _u64, _vp, _vp, _vp, _sz, _vp]),
-    "b200sort_dist_partition_planned_i32": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "b200sort_radix_copy_devn_i32": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "b200sort_dist_partition_planned_i32": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200sort_radix_copy_devn_i32": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     "b200sort_device_malloc": (_i, [ctypes.POINTER(_vp), _sz]),
     "b200sort_device_free": (_i, [_vp]),
     "b200sort_ipc_export": (_i, [_vp, _vp]),

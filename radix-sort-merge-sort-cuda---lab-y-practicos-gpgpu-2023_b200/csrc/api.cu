@@ -537,18 +537,19 @@ int b200sort_dist_plan_device(const unsigned long long *d_all_hist, int world, i
     return dist_plan_device(d_all_hist, world, rank, bits, cap, d_bin_owner, d_plan, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 int b200sort_dist_partition_planned_i32(const int32_t *d_keys, size_t n, int bits, int world, int32_t *const *h_dst_base,
-                                        const int *d_bin_owner, const void *d_plan, void *d_ws, size_t ws_bytes, void *stream) {
+                                        const int *d_bin_owner, const void *d_plan, unsigned int *d_src_hist,
+                                        void *d_ws, size_t ws_bytes, void *stream) {
     B200_TRY(device_check());
     if (n > B200SORT_MAX_N || (n > 0 && d_keys == nullptr)) return B200SORT_ERR_INVALID;
-    return dist_partition_planned(d_keys, n, bits, world, h_dst_base, d_bin_owner, d_plan, d_ws, ws_bytes,
+    return dist_partition_planned(d_keys, n, bits, world, h_dst_base, d_bin_owner, d_plan, d_src_hist, d_ws, ws_bytes,
                                   static_cast<cudaStream_t>(stream));
 }
 int b200sort_radix_copy_devn_i32(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n_max, const uint32_t *d_n,
-                                 void *d_ws, size_t ws_bytes, void *stream) {
+                                 const uint32_t *d_hist, void *d_ws, size_t ws_bytes, void *stream) {
     B200_TRY(device_check());
     if (n_max > B200SORT_MAX_N || (n_max > 0 && (d_in == nullptr || d_out == nullptr || d_tmp == nullptr)) || d_n == nullptr)
         return B200SORT_ERR_INVALID;
-    return radix_sort_devn(d_in, d_out, d_tmp, n_max, d_n, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    return radix_sort_devn(d_in, d_out, d_tmp, n_max, d_n, d_hist, d_ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 int b200sort_dist_partition_i32(const int32_t *d_keys, size_t n, int bits, int world,
                                 int32_t *const *h_dst_base, const int *d_bin_owner,

@@ -72,6 +72,7 @@ struct DistPartitionArgs {
     int32_t *dst_base[kDistMaxWorld];                  // receive buffer of every rank
     unsigned long long dst_offset[kDistMaxWorld];      // where this rank's block starts in it (host plan)
     const DistPlanDev *plan;                           // non-null: offsets (and the error flag) come from the device plan
+    unsigned int *src_hist;                            // HIST: [world][4][256] digit counts of what this rank sends where
 };
 
 // Staging area: the tile's keys grouped by destination, with up to 3 pad slots in front of every
@@ -90,7 +91,11 @@ __device__ __forceinline__ void st_stream_v4(int32_t *p, int4 v) {
 // bulk copy shared -> global per destination and tile (cp.async.bulk.global.shared::cta; the destination may be
 // a peer-mapped buffer: the copy then crosses NVLink in large posted writes); group heads and tails (<= 3 + 3
 // words) by ordinary stores.
-template <int THREADS, int OCC, int TMA = 0>
+// HIST: the four 8-bit digit histograms the destination's local sort needs are counted HERE, per destination, in
+// shared memory (4 atomics per key that hide under the NVLink-bound transfer) and added to args.src_hist when the CTA
+// is done; a reduce-scatter over the ranks then hands every rank the histogram of exactly the keys it received, and
+// its local sort skips its own histogram kernel (0.31 ms at 2^28 keys).
+template <int THREADS, int OCC, int TMA = 0, int HIST = 0>
 __global__ void __launch_bounds__(THREADS, OCC)
 dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int world,
                       const int *__restrict__ bin_owner, DistPartitionArgs args,
@@ -105,12 +110,14 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
     uint32_t *s_start = s_cnt + kDistMaxWorld;                                // [kDistMaxWorld + 2]
     unsigned long long *s_gbase = reinterpret_cast<unsigned long long *>(s_start + kDistMaxWorld + 2);
     uint8_t *s_owner = reinterpret_cast<uint8_t *>(s_gbase + kDistMaxWorld);  // [2^bits]
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_owner + ((size_t)1 << bits));   // HIST: [world][4][256]
 
     const uint32_t tid = threadIdx.x;
     const uint32_t nbins = 1u << bits;
     const int shift = 32 - bits;
     if (args.plan != nullptr && args.plan->error) return;     // some receive buffer is too small: nobody writes
     for (uint32_t i = tid; i < nbins; i += THREADS) s_owner[i] = (uint8_t)bin_owner[i];
+    if (HIST) for (uint32_t i = tid; i < (uint32_t)world * 1024u; i += THREADS) s_hist[i] = 0;
 
     const size_t tiles = (n + kTile - 1) / kTile;
     for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -134,8 +141,16 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
         for (int i = 0; i < kDistIpt; ++i) {
             const uint32_t p = i * THREADS + tid;
             if (p < valid) {
-                const uint32_t d = s_owner[key_bits(key[i]) >> shift];
+                const uint32_t kb = key_bits(key[i]);
+                const uint32_t d = s_owner[kb >> shift];
                 slot[i] = (d << 16) | atomicAdd(&s_cnt[d], 1u);
+                if (HIST) {
+                    uint32_t *h = s_hist + d * 1024u;
+                    atomicAdd(h + (kb & 255u), 1u);
+                    atomicAdd(h + 256u + ((kb >> 8) & 255u), 1u);
+                    atomicAdd(h + 512u + ((kb >> 16) & 255u), 1u);
+                    atomicAdd(h + 768u + (kb >> 24), 1u);
+                }
             }
         }
         __syncthreads();
@@ -204,6 +219,11 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
         __syncthreads();                               // the staging area is reused by the next tile
     }
     if (TMA) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (HIST) {
+        __syncthreads();
+        for (uint32_t i = tid; i < (uint32_t)world * 1024u; i += THREADS)
+            if (s_hist[i]) atomicAdd(&args.src_hist[i], s_hist[i]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -296,9 +316,9 @@ dist_plan_kernel(const unsigned long long *__restrict__ all_hist, uint32_t world
 unsigned long long dist_check_failures(unsigned long long *per_site) { return tu_check_failures(per_site); }
 size_t dist_workspace_bytes(size_t, int bits) { return 256 + (((size_t)1 << bits) + 1) * sizeof(unsigned long long); }
 
-static size_t partition_smem(int bits, int threads) {
+static size_t partition_smem(int bits, int threads, int hist_world = 0) {
     const size_t slots = (size_t)threads * kDistIpt + 4 * kDistMaxWorld;
-    return slots * 4 + slots + (kDistMaxWorld * 2 + 2) * 4 + kDistMaxWorld * 8 + ((size_t)1 << bits) + 16;
+    return slots * 4 + slots + (kDistMaxWorld * 2 + 2) * 4 + kDistMaxWorld * 8 + ((size_t)1 << bits) + 16 + (size_t)hist_world * 4096;
 }
 
 int dist_histogram(const int32_t *d_keys, size_t n, int bits, unsigned long long *d_hist, cudaStream_t s) {
@@ -353,7 +373,7 @@ int dist_plan(const unsigned long long *all_hist, int world, int rank, int bits,
 
 static int partition_launch(const int32_t *d_keys, size_t n, int bits, int world, int32_t *const *h_dst_base,
                             const int *d_bin_owner, const unsigned long long *h_dst_offset, const DistPlanDev *d_plan,
-                            void *d_ws, size_t ws_bytes, cudaStream_t s) {
+                            void *d_ws, size_t ws_bytes, cudaStream_t s, unsigned int *d_src_hist = nullptr) {
     if (bits < B200SORT_DIST_BITS_MIN || bits > B200SORT_DIST_BITS_MAX || world < 1 || world > kDistMaxWorld ||
         h_dst_base == nullptr || (h_dst_offset == nullptr && d_plan == nullptr) || d_bin_owner == nullptr)
         return B200SORT_ERR_INVALID;
@@ -365,6 +385,20 @@ static int partition_launch(const int32_t *d_keys, size_t n, int bits, int world
     std::memset(&args, 0, sizeof args);
     for (int r = 0; r < world; ++r) { args.dst_base[r] = h_dst_base[r]; args.dst_offset[r] = h_dst_offset ? h_dst_offset[r] : 0; }
     args.plan = d_plan;
+    args.src_hist = d_src_hist;
+    if (d_src_hist != nullptr) {                       // histograms ride along: the bulk-copy shape only
+        B200_CUDA_TRY(cudaMemsetAsync(d_src_hist, 0, (size_t)world * 1024 * sizeof(unsigned int), s));
+        B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(dist_partition_kernel<512, 2, 1, 1>),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)partition_smem(B200SORT_DIST_BITS_MAX, 512, kDistMaxWorld)));
+        auto *cur = static_cast<unsigned long long *>(d_ws);
+        B200_CUDA_TRY(cudaMemsetAsync(cur, 0, sizeof(unsigned long long) * kDistMaxWorld, s));
+        const size_t t = div_up(n, (size_t)512 * kDistIpt);
+        const unsigned g = (unsigned)(t < (size_t)kNumSMs * 2 ? t : (size_t)kNumSMs * 2);
+        dist_partition_kernel<512, 2, 1, 1><<<g, 512, partition_smem(bits, 512, world), s>>>(d_keys, n, bits, world, d_bin_owner, args, cur);
+        B200_LAUNCH_CHECK();
+        return B200SORT_OK;
+    }
     // Compiled shapes: 512 threads x 2 CTAs/SM (8192-key tiles), write-out by bulk copies (default) or by 128-bit
     // stores (B200SORT_DIST_TMA=0); 256 threads x 4 CTAs/SM with stores (B200SORT_DIST_SHAPE=1).
     static const int shape = [] { const char *e = getenv("B200SORT_DIST_SHAPE"); return (e && e[0] == '1') ? 1 : 0; }();
@@ -400,10 +434,11 @@ int dist_partition(const int32_t *d_keys, size_t n, int bits, int world, int32_t
 }
 
 int dist_partition_planned(const int32_t *d_keys, size_t n, int bits, int world, int32_t *const *h_dst_base,
-                           const int *d_bin_owner, const void *d_plan, void *d_ws, size_t ws_bytes, cudaStream_t s) {
+                           const int *d_bin_owner, const void *d_plan, unsigned int *d_src_hist, void *d_ws, size_t ws_bytes,
+                           cudaStream_t s) {
     if (d_plan == nullptr) return B200SORT_ERR_INVALID;
     return partition_launch(d_keys, n, bits, world, h_dst_base, d_bin_owner, nullptr, static_cast<const DistPlanDev *>(d_plan),
-                            d_ws, ws_bytes, s);
+                            d_ws, ws_bytes, s, d_src_hist);
 }
 
 int dist_plan_device(const unsigned long long *d_all_hist, int world, int rank, int bits, unsigned long long cap,

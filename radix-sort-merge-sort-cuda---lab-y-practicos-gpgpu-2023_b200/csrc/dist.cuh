@@ -27,6 +27,7 @@ int dist_partition(const int32_t *d_keys, size_t n, int bits, int world, int32_t
 int dist_plan_device(const unsigned long long *d_all_hist, int world, int rank, int bits, unsigned long long cap,
                      int *d_bin_owner, void *d_plan, void *d_ws, size_t ws_bytes, cudaStream_t s);
 int dist_partition_planned(const int32_t *d_keys, size_t n, int bits, int world, int32_t *const *h_dst_base,
-                           const int *d_bin_owner, const void *d_plan, void *d_ws, size_t ws_bytes, cudaStream_t s);
+                           const int *d_bin_owner, const void *d_plan, unsigned int *d_src_hist, void *d_ws, size_t ws_bytes,
+                           cudaStream_t s);
 
 }  // namespace b200sort

@@ -405,8 +405,10 @@ struct StepTimer {
 };
 
 int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, void *d_ws,
-                    size_t ws_bytes, cudaStream_t s, float *ms, const uint32_t *d_n = nullptr) {
-    // d_n != nullptr: n is an upper bound (grids, status rows), the kernels read the key count from *d_n
+                    size_t ws_bytes, cudaStream_t s, float *ms, const uint32_t *d_n = nullptr,
+                    const uint32_t *d_hist = nullptr) {
+    // d_n != nullptr: n is an upper bound (grids, status rows), the kernels read the key count from *d_n;
+    // d_hist != nullptr (with d_n): the four digit histograms exist already, the histogram kernel is not run
     if (ms) for (int i = 0; i < 6; ++i) ms[i] = 0.f;
     if (n == 0) return B200SORT_OK;
     if (n == 1 && d_n == nullptr) {
@@ -446,8 +448,13 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
 
     B200_CUDA_TRY(cudaMemsetAsync(ctl, 0, kRadixZeroBytes, s));
     B200_TRY(timer.begin());
-    radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_in, n, ctl, status[0], rows * kRadixBins,
-                                                                 (uint32_t)skip, in_place, d_n);
+    if (d_hist != nullptr) {
+        B200_CUDA_TRY(cudaMemsetAsync(status[0], 0, rows * kRadixBins * sizeof(uint32_t), s));
+        radix_plan_kernel<<<1, kHistThreads, 0, s>>>(d_hist, d_n, ctl, (uint32_t)skip, in_place);
+    } else {
+        radix_histogram_kernel<<<hist_grid(n), kHistThreads, kHistSmemBytes, s>>>(d_in, n, ctl, status[0], rows * kRadixBins,
+                                                                     (uint32_t)skip, in_place, d_n);
+    }
     B200_LAUNCH_CHECK();
     B200_TRY(timer.mark());
     for (int pass = 0; pass < kRadixPasses; ++pass) {
@@ -475,10 +482,10 @@ int radix_sort(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, vo
     return radix_sort_impl(d_in, d_out, d_tmp, n, d_ws, ws_bytes, s, nullptr);
 }
 
-int radix_sort_devn(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n_max, const uint32_t *d_n, void *d_ws,
-                    size_t ws_bytes, cudaStream_t s) {
+int radix_sort_devn(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n_max, const uint32_t *d_n,
+                    const uint32_t *d_hist, void *d_ws, size_t ws_bytes, cudaStream_t s) {
     if (d_n == nullptr) return B200SORT_ERR_INVALID;
-    return radix_sort_impl(d_in, d_out, d_tmp, n_max, d_ws, ws_bytes, s, nullptr, d_n);
+    return radix_sort_impl(d_in, d_out, d_tmp, n_max, d_ws, ws_bytes, s, nullptr, d_n, d_hist);
 }
 
 // ---- sort-by-key ----------------------------------------------------------------

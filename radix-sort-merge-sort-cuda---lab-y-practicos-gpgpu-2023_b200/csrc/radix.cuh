@@ -50,8 +50,10 @@ int radix_sort_pairs(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const 
 // The same sort with the key count taken from DEVICE memory (*d_n <= n_max, read by the kernels when they run):
 // lets a caller whose n is produced by an earlier kernel (the multi-GPU exchange) enqueue the sort without a
 // host synchronisation.  Grids, workspace and status rows are sized for n_max.
-int radix_sort_devn(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n_max, const uint32_t *d_n, void *d_ws,
-                    size_t ws_bytes, cudaStream_t s);
+// d_hist (may be null): uint32[4][256] digit histograms of exactly those *d_n keys, counted elsewhere -- then the
+// histogram kernel is skipped (the multi-GPU exchange counts them at the source, under the NVLink transfer).
+int radix_sort_devn(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n_max, const uint32_t *d_n,
+                    const uint32_t *d_hist, void *d_ws, size_t ws_bytes, cudaStream_t s);
 // Same, with CUDA events around every kernel: ms[0] histogram, ms[1..4] passes, ms[5] final copy.
 int radix_sort_timed(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t n, void *d_ws,
                      size_t ws_bytes, cudaStream_t s, float *ms);

@@ -49,6 +49,78 @@ __device__ __forceinline__ void hist_flush(uint32_t *sh, RadixControl *ctl, uint
     __syncthreads();
 }
 
+// What the last block of the histogram kernel does once the four digit histograms are complete: exclusive bases,
+// skippable passes, hot digits, the buffer plan.  Also run on its own (radix_plan_kernel) when the histograms were
+// counted elsewhere -- the multi-GPU exchange counts them at the source, under the NVLink transfer.
+__device__ __forceinline__ void radix_finish_plan(RadixControl *ctl, size_t n, uint32_t skip_enabled, uint32_t in_place,
+                                                  uint32_t tid, uint32_t *s_warp_sums, uint32_t *s_skip, uint32_t *s_hot)
+{
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    for (int p = 0; p < kRadixPasses; ++p) {
+        const uint32_t c = (tid < kRadixBins) ? __ldcg(&ctl->hist[p][tid]) : 0u;
+        uint32_t x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (uint32_t)o) x += y;
+        }
+        if (tid < kRadixBins && lane == 31) s_warp_sums[warp] = x;
+        __syncthreads();
+        if (tid < kRadixBins) {
+            uint32_t add = 0;
+            for (uint32_t w = 0; w < warp; ++w) add += s_warp_sums[w];
+            ctl->base[p][tid] = x - c + add;
+            if (skip_enabled && n > 0 && c == (uint32_t)n) s_skip[p] = 1;
+            if ((size_t)c * 8 > n) atomicMax(&s_hot[p], ((c >> 6) << 8) | tid);   // the most frequent such digit wins
+        }
+        __syncthreads();
+    }
+    // The buffer plan: executed pass j reads what pass j-1 wrote (the input for j = 0).
+    //   in place     : writes alternate tmp, out, tmp, ...; an odd count leaves the result in tmp
+    //                  and the final-copy kernel brings it home;
+    //   out of place : writes alternate so that the LAST executed pass lands in out; the input
+    //                  is never written.  No executed pass at all (all keys equal): copy in -> out.
+    if (tid == 0) {
+        ctl->n_dev = (uint32_t)n;
+        uint32_t executed = 0;
+        for (int p = 0; p < kRadixPasses; ++p) executed += s_skip[p] ? 0u : 1u;
+        uint32_t j = 0, cur = kSelIn;
+        for (int p = 0; p < kRadixPasses; ++p) {
+            ctl->skip[p] = s_skip[p];
+            ctl->hot[p] = s_hot[p] ? 1u + (s_hot[p] & 255u) : 0u;
+            ctl->src_sel[p] = cur;
+            uint32_t dst = cur;
+            if (!s_skip[p]) {
+                if (in_place) dst = (j % 2 == 0) ? kSelTmp : kSelOut;
+                else          dst = ((executed - 1 - j) % 2 == 0) ? kSelOut : kSelTmp;
+                ++j;
+                cur = dst;
+            }
+            ctl->dst_sel[p] = dst;
+        }
+        uint32_t final_copy = 0;
+        if (in_place) { if (cur == kSelTmp) final_copy = kSelTmp; }
+        else          { if (executed == 0) final_copy = kSelIn; }
+        ctl->final_copy = final_copy;
+    }
+}
+
+// The plan from histograms that already exist: d_hist[p][d] (uint32) = keys whose digit p is d; *d_n keys in all.
+__global__ void __launch_bounds__(kHistThreads)
+radix_plan_kernel(const uint32_t *__restrict__ d_hist, const uint32_t *d_n, RadixControl *ctl, uint32_t skip_enabled,
+                  uint32_t in_place)
+{
+    __shared__ uint32_t s_warp_sums[kRadixBins / 32];
+    __shared__ uint32_t s_skip[kRadixPasses];
+    __shared__ uint32_t s_hot[kRadixPasses];
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < kRadixPasses * kRadixBins; i += kHistThreads) ctl->hist[i >> kRadixBits][i & (kRadixBins - 1)] = d_hist[i];
+    if (tid < kRadixPasses) { s_skip[tid] = 0; s_hot[tid] = 0; }
+    __threadfence();
+    __syncthreads();
+    radix_finish_plan(ctl, (size_t)*d_n, skip_enabled, in_place, tid, s_warp_sums, s_skip, s_hot);
+}
+
 __global__ void __launch_bounds__(kHistThreads)
 radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl *ctl,
                        uint32_t *status_to_zero, size_t status_words, uint32_t skip_enabled,
@@ -122,54 +194,7 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
     if (!s_is_last) return;
     __threadfence();
 
-    const uint32_t lane = tid & 31, warp = tid >> 5;
-    for (int p = 0; p < kRadixPasses; ++p) {
-        const uint32_t c = (tid < kRadixBins) ? __ldcg(&ctl->hist[p][tid]) : 0u;
-        uint32_t x = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= (uint32_t)o) x += y;
-        }
-        if (tid < kRadixBins && lane == 31) s_warp_sums[warp] = x;
-        __syncthreads();
-        if (tid < kRadixBins) {
-            uint32_t add = 0;
-            for (uint32_t w = 0; w < warp; ++w) add += s_warp_sums[w];
-            ctl->base[p][tid] = x - c + add;
-            if (skip_enabled && n > 0 && c == (uint32_t)n) s_skip[p] = 1;
-            if ((size_t)c * 8 > n) atomicMax(&s_hot[p], ((c >> 6) << 8) | tid);   // the most frequent such digit wins
-        }
-        __syncthreads();
-    }
-    // The buffer plan: executed pass j reads what pass j-1 wrote (the input for j = 0).
-    //   in place     : writes alternate tmp, out, tmp, ...; an odd count leaves the result in tmp
-    //                  and the final-copy kernel brings it home;
-    //   out of place : writes alternate so that the LAST executed pass lands in out; the input
-    //                  is never written.  No executed pass at all (all keys equal): copy in -> out.
-    if (tid == 0) {
-        ctl->n_dev = (uint32_t)n;
-        uint32_t executed = 0;
-        for (int p = 0; p < kRadixPasses; ++p) executed += s_skip[p] ? 0u : 1u;
-        uint32_t j = 0, cur = kSelIn;
-        for (int p = 0; p < kRadixPasses; ++p) {
-            ctl->skip[p] = s_skip[p];
-            ctl->hot[p] = s_hot[p] ? 1u + (s_hot[p] & 255u) : 0u;
-            ctl->src_sel[p] = cur;
-            uint32_t dst = cur;
-            if (!s_skip[p]) {
-                if (in_place) dst = (j % 2 == 0) ? kSelTmp : kSelOut;
-                else          dst = ((executed - 1 - j) % 2 == 0) ? kSelOut : kSelTmp;
-                ++j;
-                cur = dst;
-            }
-            ctl->dst_sel[p] = dst;
-        }
-        uint32_t final_copy = 0;
-        if (in_place) { if (cur == kSelTmp) final_copy = kSelTmp; }
-        else          { if (executed == 0) final_copy = kSelIn; }
-        ctl->final_copy = final_copy;
-    }
+    radix_finish_plan(ctl, n, skip_enabled, in_place, tid, s_warp_sums, s_skip, s_hot);
 }
 
 

@@ -96,6 +96,13 @@ class DistSorter:
         self.part_ws = torch.zeros(self.part_ws_bytes + 256, dtype=torch.uint8, device=self.dev)
         self.part_ws_ptr = self.part_ws.data_ptr() + (-self.part_ws.data_ptr()) % 256
         self.plan_dev = torch.zeros(PLAN_BYTES // 8, dtype=torch.int64, device=self.dev)     # the device plan record
+        # digit histograms counted at the source: [destination][4][256], and the row that is mine after the reduce-scatter
+        self.src_hist = torch.zeros(self.world * 1024, dtype=torch.int32, device=self.dev)
+        self.my_hist = torch.zeros(1024, dtype=torch.int32, device=self.dev)
+        # Worth it where the exchange is bound by the fabric, not by the partition kernel (4+ GPUs): the four shared-memory
+        # atomics per key cost the kernel 0.4 ms at 2^28 keys, which 2 GPUs do not hide (measured: 4.43 ms either way).
+        env = os.environ.get("B200SORT_DIST_HIST_AT_SOURCE")
+        self.hist_at_source = (env != "0") if env is not None else (self.world >= 4)
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.peer_ptrs = [None] * self.world
         self.send = None
@@ -185,15 +192,24 @@ class DistSorter:
             mark()
             # phase 3: the kernel's bulk copies into the peers' receive buffers ARE the exchange
             base = (ctypes.c_void_p * self.world)(*self.peer_ptrs)
+            hist = self.hist_at_source
             check(L.b200sort_dist_partition_planned_i32(keys.data_ptr(), n, self.bits, self.world, base,
                                                         self.owner_dev.data_ptr(), self.plan_dev.data_ptr(),
+                                                        self.src_hist.data_ptr() if hist else None,
                                                         self.part_ws_ptr, self.part_ws_bytes, stream))
-            # stream-ordered barrier: nobody sorts before every peer's stores have landed
-            dist.all_reduce(self.flag, group=self.group)
+            # stream-ordered barrier: nobody sorts before every peer's stores have landed.  With the digit histograms
+            # counted at the source the barrier carries them: a reduce-scatter hands every rank the histogram of
+            # exactly the keys it received, and its local sort skips its own histogram kernel.
+            if hist:
+                dist.reduce_scatter_tensor(self.my_hist, self.src_hist, group=self.group)
+            else:
+                dist.all_reduce(self.flag, group=self.group)
             mark()
             # phase 4: the key count comes from the device record
             check(L.b200sort_radix_copy_devn_i32(self.recv_ptr, self.out.data_ptr(), self.tmp.data_ptr(), self.cap,
-                                                 self.plan_dev.data_ptr() + PLAN_M_OFFSET, self.ws_ptr, self.ws_bytes, stream))
+                                                 self.plan_dev.data_ptr() + PLAN_M_OFFSET,
+                                                 self.my_hist.data_ptr() if hist else None,
+                                                 self.ws_ptr, self.ws_bytes, stream))
             mark()
             return self.out
         # ---- the NCCL all-to-all baseline: host planner (the collective needs the split sizes on the host) ----

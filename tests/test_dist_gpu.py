@@ -5,6 +5,8 @@ import ctypes
 import numpy as np
 import pytest
 
+import oracle
+
 from b200sort import datagen
 from b200sort import dist as b200dist
 from b200sort._lib import check, lib
@@ -112,13 +114,15 @@ def test_sync_free_path_with_simulated_ranks(world, dist_name):
     nb = L.b200sort_dist_workspace_bytes(0, bits)
     ws = torch.zeros(nb + 256, dtype=torch.uint8, device="cuda")
     ws_ptr = ws.data_ptr() + (-ws.data_ptr()) % 256
-    recs = []
+    recs, src_hists = [], []
     for s in range(world):
         *_, owner_t, rec_t = _device_plan(all_hist, world, s, bits, cap)
         recs.append(rec_t)
         d = to_device(srcs[s])
+        src_hists.append(torch.full((world * 1024,), -1, dtype=torch.int32, device="cuda"))
         check(L.b200sort_dist_partition_planned_i32(d.data_ptr(), d.numel(), bits, world, base, owner_t.data_ptr(),
-                                                    rec_t.data_ptr(), ws_ptr, nb, stream_ptr()))
+                                                    rec_t.data_ptr(), src_hists[-1].data_ptr(),
+                                                    ws_ptr, nb, stream_ptr()))
         torch.cuda.synchronize()
     everything = np.concatenate(srcs)
     top = (everything.view(np.uint32) ^ np.uint32(0x80000000)) >> np.uint32(32 - bits)
@@ -128,10 +132,14 @@ def test_sync_free_path_with_simulated_ranks(world, dist_name):
     sws = torch.empty(wsb + 256, dtype=torch.uint8, device="cuda")
     sws_ptr = sws.data_ptr() + (-sws.data_ptr()) % 256
     for r in range(world):
-        out = torch.full((cap,), -9, dtype=torch.int32, device="cuda"); tmp = torch.empty_like(out)
-        check(L.b200sort_radix_copy_devn_i32(bufs[r].data_ptr(), out.data_ptr(), tmp.data_ptr(), cap,
-                                             recs[r].data_ptr() + PLAN_M_OFFSET, sws_ptr, wsb, stream_ptr()))
-        torch.cuda.synchronize()
         m = int(recv_h[r])
         want = np.sort(everything[dest == r])
-        assert out.cpu().numpy()[:m].tobytes() == want.tobytes(), (world, dist_name, r)
+        # what a reduce-scatter over the ranks would hand rank r: the digit histograms of exactly the keys it received
+        mine = torch.stack([h.view(world, 1024)[r] for h in src_hists]).sum(0).to(torch.int32).contiguous()
+        assert (mine.cpu().numpy().astype(np.uint64).reshape(4, 256) == oracle.digit_histograms(want)).all(), (world, dist_name, r)
+        for d_hist in (None, mine.data_ptr()):            # the local sort with its own histogram kernel, and without
+            out = torch.full((cap,), -9, dtype=torch.int32, device="cuda"); tmp = torch.empty_like(out)
+            check(L.b200sort_radix_copy_devn_i32(bufs[r].data_ptr(), out.data_ptr(), tmp.data_ptr(), cap,
+                                                 recs[r].data_ptr() + PLAN_M_OFFSET, d_hist, sws_ptr, wsb, stream_ptr()))
+            torch.cuda.synchronize()
+            assert out.cpu().numpy()[:m].tobytes() == want.tobytes(), (world, dist_name, r, d_hist is not None)

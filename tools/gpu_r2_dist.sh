@@ -4,6 +4,12 @@ N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/r02_topo_${N}.txt 2>&1
 echo "== multi-device tests"; timeout 1200 python -m pytest tests/test_multi_device_gpu.py -x -q 2>&1 | tail -6
+if [ "$N" -ge 4 ]; then
+  echo "== bench weak x$N, digit histograms by the local sort's own kernel (B200SORT_DIST_HIST_AT_SOURCE=0)"
+  B200SORT_DIST_HIST_AT_SOURCE=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29523 bench.py --gpus $N --steps 20 --warmup 3 --no-configs 2>/dev/null | tail -1 > gpurun_out/r02_bench_dist_${N}_hist_local.json
+  python -c "
+import json; j=json.loads(open('gpurun_out/r02_bench_dist_${N}_hist_local.json').read()); print('  ms', round(j['ms_per_step'],3), 'Gkeys/s', round(j['value']/1e9,1), {k: round(v,3) for k,v in j['roofline']['phases_max_over_ranks'].items()})"
+fi
 echo "== bench weak x$N"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 20 --warmup 3 2> gpurun_out/r02_bench_dist_${N}.err | tail -1 > gpurun_out/r02_bench_dist_${N}.json
 python - <<PY
 import json
