@@ -148,8 +148,7 @@ dist_partition_kernel(const int32_t *__restrict__ keys, size_t n, int bits, int 
                     uint32_t *h = s_hist + d * 1024u;
                     atomicAdd(h + (kb & 255u), 1u);
                     atomicAdd(h + 256u + ((kb >> 8) & 255u), 1u);
-                    atomicAdd(h + 512u + ((kb >> 16) & 255u), 1u);
-                    atomicAdd(h + 768u + (kb >> 24), 1u);
+                    atomicAdd(h + 512u + ((kb >> 16) & 255u), 1u);     // the top byte's histogram follows from the bin counts
                 }
             }
         }
@@ -290,6 +289,16 @@ dist_plan_kernel(const unsigned long long *__restrict__ all_hist, uint32_t world
         uint32_t o = 0;
         for (uint32_t k = 1; k < world; ++k) o += (s_bound[k] <= b) ? 1u : 0u;
         bin_owner[b] = (int)o;
+    }
+    if (tid < 256) {                                   // top-byte histogram of this rank's range: bins t*2^(bits-8) .. of byte t
+        const uint32_t per_byte = nbins >> 8, lo = s_bound[rank], hi = s_bound[rank + 1];
+        uint32_t c = 0;
+        if (per_byte > 0) {
+            const uint32_t a = tid * per_byte > lo ? tid * per_byte : lo;
+            const uint32_t b = (tid + 1) * per_byte < hi ? (tid + 1) * per_byte : hi;
+            if (b > a) c = (uint32_t)(cum[b] - cum[a]);
+        }
+        plan->top_hist[tid] = c;
     }
     if (tid < world) {
         const unsigned long long rc = cum[s_bound[tid + 1]] - cum[s_bound[tid]];

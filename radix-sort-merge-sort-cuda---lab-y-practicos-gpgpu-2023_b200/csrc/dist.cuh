@@ -12,6 +12,7 @@ struct DistPlanDev {
     unsigned int m;                                           // recv_count[this rank], for the local sort
     unsigned int error;                                       // 1: some rank would receive more than its buffer holds
     unsigned int pad[2];
+    unsigned int top_hist[256];                               // top-byte histogram of the keys this rank will own
 };
 static_assert(sizeof(DistPlanDev) == B200SORT_DIST_PLAN_BYTES, "include/b200sort.h states the size of the plan record");
 

@@ -34,7 +34,8 @@ import numpy as np
 from ._lib import ALGO_RADIX, check, lib
 
 DEFAULT_BITS = 14          # 2^14 bins: a byte that holds 90 % of the keys still splits within 6 % of a rank's share
-PLAN_BYTES = 400           # B200SORT_DIST_PLAN_BYTES
+PLAN_BYTES = 1424          # B200SORT_DIST_PLAN_BYTES
+PLAN_TOP_HIST_OFFSET = 400 # uint32 top_hist[256]
 PLAN_M_OFFSET = 384        # uint32 m, then uint32 error
 
 
@@ -102,7 +103,7 @@ class DistSorter:
         # Worth it where the exchange is bound by the fabric, not by the partition kernel (4+ GPUs): the four shared-memory
         # atomics per key cost the kernel 0.4 ms at 2^28 keys, which 2 GPUs do not hide (measured: 4.43 ms either way).
         env = os.environ.get("B200SORT_DIST_HIST_AT_SOURCE")
-        self.hist_at_source = (env != "0") if env is not None else (self.world >= 4)
+        self.hist_at_source = ((env != "0") if env is not None else (self.world >= 4)) and bits >= 8 and exchange == "p2p"
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.peer_ptrs = [None] * self.world
         self.send = None
@@ -202,6 +203,8 @@ class DistSorter:
             # exactly the keys it received, and its local sort skips its own histogram kernel.
             if hist:
                 dist.reduce_scatter_tensor(self.my_hist, self.src_hist, group=self.group)
+                # digits 0..2 were counted at the source; the top byte's histogram follows from the bin counts (plan)
+                self.my_hist[768:].copy_(self.plan_dev.view(torch.int32)[PLAN_TOP_HIST_OFFSET // 4:PLAN_TOP_HIST_OFFSET // 4 + 256])
             else:
                 dist.all_reduce(self.flag, group=self.group)
             mark()

@@ -57,7 +57,7 @@ def test_partition_kernel_with_simulated_ranks(world, dist_name):
         assert got.tobytes() == want.tobytes(), (world, dist_name, r)
 
 
-PLAN_BYTES, PLAN_M_OFFSET = 400, 384
+PLAN_BYTES, PLAN_M_OFFSET, PLAN_TOP_OFFSET = 1424, 384, 400
 
 
 def _device_plan(all_hist, world, rank, bits, cap):
@@ -136,6 +136,8 @@ def test_sync_free_path_with_simulated_ranks(world, dist_name):
         want = np.sort(everything[dest == r])
         # what a reduce-scatter over the ranks would hand rank r: the digit histograms of exactly the keys it received
         mine = torch.stack([h.view(world, 1024)[r] for h in src_hists]).sum(0).to(torch.int32).contiguous()
+        assert int(mine[768:].abs().sum().item()) == 0              # the top byte is not counted at the source ...
+        mine[768:] = recs[r].view(torch.int32)[PLAN_TOP_OFFSET // 4:PLAN_TOP_OFFSET // 4 + 256]   # ... it follows from the plan
         assert (mine.cpu().numpy().astype(np.uint64).reshape(4, 256) == oracle.digit_histograms(want)).all(), (world, dist_name, r)
         for d_hist in (None, mine.data_ptr()):            # the local sort with its own histogram kernel, and without
             out = torch.full((cap,), -9, dtype=torch.int32, device="cuda"); tmp = torch.empty_like(out)
