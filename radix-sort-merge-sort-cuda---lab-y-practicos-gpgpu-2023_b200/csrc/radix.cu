@@ -102,13 +102,14 @@ const Variant kVariants[] = {
       Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 1>,
       radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 1, 0, 1> },   //  2: the documented-
                                                //     behaviour fallback: the default kernel ranked by ballots
+#ifdef B200SORT_EXPERIMENTS
+    // ---- every other shape measured in rounds 1-2 (profiles/r0*_onesweep_variants.md): make EXPERIMENTS=1 ----------
+    // (the phase-timing twins of shapes 0 and 1, round 1's default and round 1's fallback come first)
     { "TIMING_tma_16w_ipt20", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes, radix_onesweep_tma_kernel<1> },   //  3
     { "TIMING_pipelined2_ipt20_pack", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
       Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 1, 0, 1, 2, 0, 0, 1> },   //  4
     B200_PP2X_VARIANT(20, 0, 1),               //  5: variant 0 with the ticket drawn before the look-back (round 1's default)
     B200_VARIANT(16, 16, 2, kRankBallot, 1),   //  6: one tile per CTA, ballot-ranked (round 1's fallback)
-#ifdef B200SORT_EXPERIMENTS
-    // ---- every other shape measured in rounds 1-2 (profiles/r0*_onesweep_variants.md): make EXPERIMENTS=1 ----------
     { "pipelined2_16w_ipt22_kRankAdd_pack1_late_ticket", kRankAdd, 0, 1, 512, Pipelined2Shape<22, 1>::kTile,
       Pipelined2Shape<22, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<22, 0, 0, 1, 2, 0, 0, 1> },   //  7: 11264-key tiles
     { "pipelined2_16w_ipt24_kRankAdd_pack1_late_ticket", kRankAdd, 0, 1, 512, Pipelined2Shape<24, 1>::kTile,
@@ -514,7 +515,11 @@ int launch_pairs_passes(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, con
     return B200SORT_OK;
 }
 int pairs_ipt() {
+#ifdef B200SORT_EXPERIMENTS
     static const int v = [] { const char *e = getenv("B200SORT_PAIRS_IPT"); return (e && atoi(e) == 12) ? 12 : 10; }();
+#else
+    static const int v = 10;
+#endif
     return v;
 }
 size_t radix_pairs_tile() { return 512u * (size_t)(atomic_order_ok() ? pairs_ipt() : 10); }
@@ -546,7 +551,9 @@ int radix_sort_pairs(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, const 
                                                                  (uint32_t)skip, in_place);
     B200_LAUNCH_CHECK();
     if (safe)                   B200_TRY((launch_pairs_passes<10, 1>(d_in, d_out, d_tmp, v_in, v_out, v_tmp, n, ctl, status, s)));
+#ifdef B200SORT_EXPERIMENTS
     else if (pairs_ipt() == 12) B200_TRY((launch_pairs_passes<12, 0>(d_in, d_out, d_tmp, v_in, v_out, v_tmp, n, ctl, status, s)));
+#endif
     else                        B200_TRY((launch_pairs_passes<10, 0>(d_in, d_out, d_tmp, v_in, v_out, v_tmp, n, ctl, status, s)));
     if (skip) {
         const size_t blocks = div_up(div_up(n, 4), 256);
