@@ -26,6 +26,7 @@
 #include "radix_tile.cuh"
 #include "radix_pipelined.cuh"
 #include "radix_tma.cuh"
+#include "radix_tma2.cuh"
 #include "radix_misc.cuh"
 #include "radix_small.cuh"
 
@@ -102,6 +103,10 @@ const Variant kVariants[] = {
       Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 1>,
       radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 1, 0, 1> },   //  2: the documented-
                                                //     behaviour fallback: the default kernel ranked by ballots
+    { "tma2_16w_2x16_kRankAdd_tmem_keys_second_atomic_bulk_store", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT2SmemBytes,
+      radix_onesweep_tma2_kernel<0>, radix_onesweep_tma2_kernel<0, 1> },   //  3: 16384-key tiles, keys only in tensor memory,
+                                               //     positions by a second atomic, TMA write-out
+    { "TIMING_tma2_16w_2x16", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT2SmemBytes, radix_onesweep_tma2_kernel<1> },   //  4
 #ifdef B200SORT_EXPERIMENTS
     // ---- every other shape measured in rounds 1-2 (profiles/r0*_onesweep_variants.md): make EXPERIMENTS=1 ----------
     // (the phase-timing twins of shapes 0 and 1, round 1's default and round 1's fallback come first)

@@ -43,6 +43,16 @@ __device__ __forceinline__ uint32_t walk_back_prefetched(const uint32_t *win, ui
         uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) w[j] = (base + j < have) ? win[(have - 1 - base - j) * kRadixBins] : 0u;
+        if (base + 8 <= have) {
+            // fast path: eight rows that are all "published, not inclusive" (flag 01) are added whole -- their eight
+            // flags add up to 2^33, i.e. to nothing in 32 bits
+            const uint32_t all_and = w[0] & w[1] & w[2] & w[3] & w[4] & w[5] & w[6] & w[7];
+            const uint32_t all_or  = w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7];
+            if ((all_and >> 30) == 1u && (all_or >> 30) == 1u) {
+                acc += (w[0] + w[1]) + (w[2] + w[3]) + ((w[4] + w[5]) + (w[6] + w[7]));
+                continue;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (base + j < have) {
@@ -56,6 +66,5 @@ __device__ __forceinline__ uint32_t walk_back_prefetched(const uint32_t *win, ui
     if (max_dist > have) acc += walk_back<W>(first - (size_t)have * kRadixBins, max_dist - have);
     return acc;
 }
-
 
 }  // namespace b200sort

@@ -16,7 +16,7 @@ src = torch.randint(-2**31, 2**31, (n,), dtype=torch.int64, device="cuda", gener
 out = torch.empty_like(src)
 wsb = L.b200sort_workspace_bytes(n, ALGO_RADIX)
 ws = torch.empty(wsb + 256, dtype=torch.uint8, device="cuda"); wp = ws.data_ptr() + (-ws.data_ptr()) % 256
-dbg = torch.zeros(tiles * 2 * 16, dtype=torch.int64, device="cuda")
+dbg = torch.zeros((tiles + 1) * 2 * 16, dtype=torch.int64, device="cuda")   # + a dummy row
 s = torch.cuda.current_stream().cuda_stream
 for rep in range(2):
     check(L.b200sort_radix_pass_i32(src.data_ptr(), out.data_ptr(), n, 1, wp, wsb, s))
@@ -25,7 +25,7 @@ check(L.b200sort_debug_set_phase_buffer(dbg.data_ptr()))
 check(L.b200sort_radix_pass_i32(src.data_ptr(), out.data_ptr(), n, 1, wp, wsb, s))
 torch.cuda.synchronize()
 check(L.b200sort_debug_set_phase_buffer(None))
-d = dbg.cpu().numpy().reshape(tiles, 2, 16).astype(np.float64)
+d = dbg.cpu().numpy().reshape(tiles + 1, 2, 16)[:tiles].astype(np.float64)
 mid = d[tiles // 8: tiles * 7 // 8]
 mid = mid[(mid[:, 0, 7] > 0) & (mid[:, 1, 7] > 0) & (mid[:, 1, 10] > 0)]
 names = {0: "keys in regs", 1: "ranked+parked", 2: "SYNC1", 3: "digit group done", 4: "SYNC2", 5: "staged", 6: "SYNC3", 7: "prev written"}
