@@ -27,6 +27,7 @@
 #include "radix_pipelined.cuh"
 #include "radix_tma.cuh"
 #include "radix_tma2.cuh"
+#include "radix_tma3.cuh"
 #include "radix_misc.cuh"
 #include "radix_small.cuh"
 
@@ -91,25 +92,33 @@ struct Variant {
 
 const Variant kVariants[] = {
     // ---- the shipped shapes ------------------------------------------------------------------------------------
+    { "tma3_16w_2x16_kRankAdd_tmem_keys_bulk_store_staggered", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes,
+      radix_onesweep_tma3_kernel<0>, radix_onesweep_tma3_kernel<0, 1> },   //  0: DEFAULT: persistent CTAs, 16384-key
+                                               //     tiles, keys parked in tensor memory, positions from a second shared
+                                               //     atomic, write-out by TMA bulk copies, the halves of the CTA out of
+                                               //     step, the next tiles prefetched into L2 by the TMA unit.  As the default
+                                               //     CONFIGURATION (radix_sort_impl) arrays below 2^24 keys run shape 1.
     { "pipelined2_16w_ipt20_kRankAdd_pack1_late_ticket", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
       Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1>,
-      radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 0, 0, 1> },   //  0: DEFAULT: persistent
-                                               //     CTAs, 10240-key tiles, delayed two-level look-back, 16-bit counters (two
-                                               //     warps per row), ticket drawn after the look-back, write-out by the
-                                               //     load/store pipe
-    { "tma_16w_ipt20_kRankAdd_tmem_parked_bulk_store", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes,
-      radix_onesweep_tma_kernel<0> },          //  1: keys parked in tensor memory, late co-aligned staging, TMA write-out
+      radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 0, 0, 1> },   //  1: the ALTERNATE: 10240-key tiles,
+                                               //     delayed two-level look-back, 16-bit counters (two warps per row),
+                                               //     ticket drawn after the look-back, write-out by the load/store pipe
     { "pipelined2_16w_ipt20_kRankBallot_pack1_late_ticket", kRankBallot, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
       Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 1>,
       radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 1, 0, 1> },   //  2: the documented-
-                                               //     behaviour fallback: the default kernel ranked by ballots
-    { "tma2_16w_2x16_kRankAdd_tmem_keys_second_atomic_bulk_store", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT2SmemBytes,
-      radix_onesweep_tma2_kernel<0>, radix_onesweep_tma2_kernel<0, 1> },   //  3: 16384-key tiles, keys only in tensor memory,
-                                               //     positions by a second atomic, TMA write-out
-    { "TIMING_tma2_16w_2x16", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT2SmemBytes, radix_onesweep_tma2_kernel<1> },   //  4
+                                               //     behaviour fallback: shape 1 ranked by ballots
+    { "tma3_16w_2x16_kRankAdd_tmem_keys_bulk_store_staggered_any_size", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes,
+      radix_onesweep_tma3_kernel<0>, radix_onesweep_tma3_kernel<0, 1> },   //  3: shape 0 whatever the size
 #ifdef B200SORT_EXPERIMENTS
     // ---- every other shape measured in rounds 1-2 (profiles/r0*_onesweep_variants.md): make EXPERIMENTS=1 ----------
-    // (the phase-timing twins of shapes 0 and 1, round 1's default and round 1's fallback come first)
+    // (the phase-timing twins, the earlier TMA kernels, round 1's default and round 1's fallback come first)
+    { "TIMING_tma3_16w_2x16", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes, radix_onesweep_tma3_kernel<1> },
+    { "tma_16w_ipt20_kRankAdd_tmem_parked_bulk_store", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes,
+      radix_onesweep_tma_kernel<0> },          //     keys + ranks parked in tensor memory, late co-aligned staging, TMA write-out
+    { "tma2_16w_2x16_kRankAdd_tmem_keys_second_atomic_bulk_store", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT2SmemBytes,
+      radix_onesweep_tma2_kernel<0>, radix_onesweep_tma2_kernel<0, 1> },   //     16384-key tiles, keys only in tensor memory,
+                                               //     positions by a second atomic, TMA write-out, all warps in step
+    { "TIMING_tma2_16w_2x16", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT2SmemBytes, radix_onesweep_tma2_kernel<1> },
     { "TIMING_tma_16w_ipt20", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes, radix_onesweep_tma_kernel<1> },   //  3
     { "TIMING_pipelined2_ipt20_pack", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
       Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 1, 0, 1, 2, 0, 0, 1> },   //  4
@@ -197,6 +206,10 @@ const Variant kVariants[] = {
 #endif
 };
 constexpr int kFallbackVariant = 2;
+constexpr int kSmallTileVariant = 1;
+// Below this many keys the default configuration runs shape 1: its smaller tiles fill the machine earlier
+// (profiles/r02_size_sweep.txt: 0.146 against 0.144 ms at 2^22, 0.290 against 0.273 ms at 2^24).
+constexpr size_t kDefaultMinKeys = (size_t)1 << 23;
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 std::atomic<int> g_variant{0};
@@ -436,6 +449,7 @@ int radix_sort_impl(const int32_t *d_in, int32_t *d_out, int32_t *d_tmp, size_t 
     }
     int v = effective_variant();
     if (d_n != nullptr && kVariants[v].fn_devn == nullptr) v = atomic_order_ok() ? 0 : kFallbackVariant;
+    if (v == 0 && n < kDefaultMinKeys) v = kSmallTileVariant;
     B200_TRY(ensure_smem_attr(v));
     if (d_n != nullptr)
         B200_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(kVariants[v].fn_devn),

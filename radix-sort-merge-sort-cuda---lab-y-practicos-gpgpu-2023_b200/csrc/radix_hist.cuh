@@ -1,6 +1,7 @@
 // radix_hist.cuh -- k1: the digit-histogram kernel of the onesweep radix sort (included by radix.cu).
 #pragma once
 #include "radix.cuh"
+#include "radix_async.cuh"
 
 #include <cooperative_groups.h>
 
@@ -162,6 +163,13 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
     constexpr size_t kChunk = (size_t)kHistThreads * kHistUnroll;
     int iters = 0;
     for (size_t base = (size_t)blockIdx.x * kChunk; base < nvec; base += (size_t)gridDim.x * kChunk) {
+        // the chunk this CTA reads next is sent for (TMA prefetch into L2): three CTAs of this size leave an SM 60 KB of
+        // L1, which bounds the loads in flight, so L2 hits instead of HBM reads are what lifts the load rate
+        if (tid == 0) {
+            const size_t far = base + (size_t)gridDim.x * kChunk;
+            if (far < nvec)
+                bulk_prefetch_l2(v + far, (uint32_t)((nvec - far < kChunk ? nvec - far : kChunk) * sizeof(int4)));
+        }
         int4 r[kHistUnroll];
         bool ok[kHistUnroll];
 #pragma unroll

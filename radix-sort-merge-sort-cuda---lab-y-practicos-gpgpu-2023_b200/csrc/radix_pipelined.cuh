@@ -797,7 +797,22 @@ radix_onesweep_pipelined2_body(const int32_t *in_buf, int32_t *out_buf, int32_t 
             __syncwarp();
             // LATE: the next tile's ticket is drawn AFTER the look-back (the one phase whose length varies), so that
             // from ticket to publication every tile takes the same time and tiles_f() are published in ticket order
-            if (LATE && tid == kRadixBins) s_misc[8 + ((iter + 1) & 1)] = atomicAdd(&ctl->ticket[pass], 1u);
+            if (LATE && tid == kRadixBins) {
+                const uint32_t t_next = atomicAdd(&ctl->ticket[pass], 1u);
+                s_misc[8 + ((iter + 1) & 1)] = t_next;
+                // ... and the tile some CTA will draw half a round of tickets from now is sent for (TMA prefetch into L2):
+                // the loads an SM can have in flight are bounded by the L1 its CTAs' shared memory leaves (60 KB here),
+                // so how long a load is in flight -- HBM or L2 -- bounds how fast the keys come in
+                const size_t t_far = (size_t)t_next + gridDim.x / 2;
+                if (t_far < tiles_f()) {
+                    const size_t left = (n_f() - t_far * kTile) * 4;
+                    const uint32_t bytes = (uint32_t)((left < (size_t)kTile * 4 ? left : (size_t)kTile * 4) & ~(size_t)15);
+                    if (bytes > 0) {
+                        bulk_prefetch_l2(reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(in + t_far * kTile) & ~(uintptr_t)15), bytes);
+                        if (KV) bulk_prefetch_l2(reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(vin + t_far * kTile) & ~(uintptr_t)15), bytes);
+                    }
+                }
+            }
             if (OVL) bar_sync(11, 512);                       // group A's positions are final
             B200_STAMP(3);                                    // group B done
         }

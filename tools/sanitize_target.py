@@ -93,8 +93,11 @@ if L.b200sort_debug_checked_build():
         same(gpu_sort(k, ALGO_RADIX), oracle.radix_sort(k), f"radix default n=2^24+4321 {dist_name}")
     check(L.b200sort_radix_set_variant(1))
     k = datagen.uniform((1 << 24) + 4321, 9)
-    same(gpu_sort(k, ALGO_RADIX), oracle.radix_sort(k), "radix TMA shape n=2^24+4321 uniform")
+    same(gpu_sort(k, ALGO_RADIX), oracle.radix_sort(k), "radix small-tile shape n=2^24+4321 uniform")
     check(L.b200sort_radix_set_variant(0))
+    for dist_name in ("zipf16", "and3", "edge_mix"):
+        k = datagen.make(dist_name, (1 << 23) + 77, 10)
+        same(gpu_sort(k, ALGO_RADIX), oracle.radix_sort(k), f"radix default n=2^23+77 {dist_name}")
     sites = (ctypes.c_ulonglong * 16)()
     fails = int(L.b200sort_debug_check_failures_by_site(ctypes.cast(sites, ctypes.c_void_p)))
     print('per check site:', list(sites), flush=True)
