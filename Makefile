@@ -6,6 +6,7 @@
 #                      performanceTest.cpp (compiled from where they lie) linked against the product;
 #                      build/b200sort_driver: this repo's checked, parameterised driver
 #   make ptxas      -> register / shared-memory report of every kernel
+#   make checked / make experiments -> self-asserting library / library with every measured shape (see below)
 
 PKG     := radix-sort-merge-sort-cuda---lab-y-practicos-gpgpu-2023_b200
 CSRC    := $(PKG)/csrc
@@ -43,6 +44,15 @@ build/obj_checked/%.o: $(CSRC)/%.cu $(HDRS)
 checked: $(COBJS)
 	$(NVCC) $(ARCH) -shared -o "$(PKG)/libb200sort_checked.so" $(COBJS)
 
+# make experiments -> <pkg>/libb200sort_exp.so: the product plus every shape that was measured and lost and the
+# phase-timing twins (B200SORT_LIB=libb200sort_exp.so python tools/phase_timing_tma.py TIMING_tma3)
+EOBJS := $(patsubst $(CSRC)/%.cu,build/obj_exp/%.o,$(SRCS))
+build/obj_exp/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build/obj_exp
+	$(NVCC) $(NVFLAGS) -DB200SORT_EXPERIMENTS -c "$<" -o "$@"
+experiments: $(EOBJS)
+	$(NVCC) $(ARCH) -shared -o "$(PKG)/libb200sort_exp.so" $(EOBJS)
+
 oracle:
 	$(MAKE) -C oracle all
 	$(MAKE) -C oracle ref
@@ -64,6 +74,6 @@ ptxas:
 	@for f in $(SRCS); do echo "== $$f"; $(NVCC) $(NVFLAGS) -Xptxas -v -c "$$f" -o /dev/null 2>&1 | grep -E "Compiling|registers|spill" ; done
 
 clean:
-	rm -rf build $(LIB) $(PKG)/libb200sort_checked.so
+	rm -rf build $(LIB) $(PKG)/libb200sort_checked.so $(PKG)/libb200sort_exp.so
 
-.PHONY: all oracle drivers ptxas clean checked
+.PHONY: all oracle drivers ptxas clean checked experiments

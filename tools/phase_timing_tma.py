@@ -39,7 +39,7 @@ if b"tma3" in want:
             print(f"  {nm[i-1]:>18s} -> {nm[i]:<18s} mean {dt.mean():8.0f} cyc   p50 {np.median(dt):8.0f}   p90 {np.percentile(dt, 90):8.0f}")
         tot = mid[:, grp, 7] - mid[:, grp, 0]
         print(f"  iteration mean {tot.mean():.0f} cyc ({tot.mean()/1.965e3:.2f} us)")
-    for a, b2, label in ((0, 11, "start -> fetched rows landed (mbarrier)"), (11, 10, "look-back sums"), (10, 1, "start words added to the counters")):
+    for a, b2, label in ((0, 11, "start -> fetched rows landed (mbarrier)"), (11, 12, "sums over the fetched rows"), (12, 10, "walks beyond the fetched rows (global)"), (10, 1, "start words added to the counters")):
         dt = mid[:, 1, b2] - mid[:, 1, a]
         print(f"group B: {label:<48s} mean {dt.mean():8.0f} cyc   p50 {np.median(dt):8.0f}   p90 {np.percentile(dt, 90):8.0f}   max {dt.max():8.0f}")
     sys.exit(0)
