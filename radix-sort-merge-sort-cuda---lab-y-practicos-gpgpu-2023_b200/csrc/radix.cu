@@ -113,6 +113,8 @@ const Variant kVariants[] = {
     // ---- every other shape measured in rounds 1-2 (profiles/r0*_onesweep_variants.md): make EXPERIMENTS=1 ----------
     // (the phase-timing twins, the earlier TMA kernels, round 1's default and round 1's fallback come first)
     { "TIMING_tma3_16w_2x16", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes, radix_onesweep_tma3_kernel<1> },
+    { "tma3_16w_2x16_kRankAdd_in_step", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes, radix_onesweep_tma3_kernel<0, 0, 1> },
+    { "TIMING_tma3i_16w_2x16", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes, radix_onesweep_tma3_kernel<1, 0, 1> },
     { "tma_16w_ipt20_kRankAdd_tmem_parked_bulk_store", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes,
       radix_onesweep_tma_kernel<0> },          //     keys + ranks parked in tensor memory, late co-aligned staging, TMA write-out
     { "tma2_16w_2x16_kRankAdd_tmem_keys_second_atomic_bulk_store", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT2SmemBytes,

@@ -15,38 +15,43 @@ namespace b200sort {
 constexpr int kHistThreads = 512;
 constexpr int kHistUnroll  = 4;                  // 128-bit loads in flight per thread
 constexpr int kHistBlocksPerSM = 3;
-// Shared-memory counters are 16-bit and LANE-PRIVATE: counter (place p, digit d, lane l) lives in
-// half (l & 1) of word (p*256 + d)*16 + (l >> 1).  The bank is 16*(d & 1) + (l >> 1), so the only
-// lanes that can ever collide in one atomic instruction are the two lanes of a pair -- at most
-// 2 wavefronts whatever the key distribution (32 random words on 32 banks cost ~3.5, and an
-// all-equal input would serialise 32 ways).  16-bit counters overflow after 65535 hits, so the
-// block flushes to the global histogram every kHistFlushIters iterations (<= 32768 hits each).
-constexpr int kHistSmemWords  = kRadixPasses * kRadixBins * 16;                  // 64 KiB
+// Shared-memory counters are 16-bit and LANE-PRIVATE: counter (place p, digit d, lane l) lives in half (p & 1) of
+// word ((p >> 1) * 256 + d) * 32 + l.  The bank is l: no two lanes of an atomic instruction ever meet, whatever the
+// key distribution -- one wavefront per instruction (32 random words on 32 banks cost ~3.5; round 1's layout, two
+// lanes per word, cost 2.2 and held the kernel at 91 % of the load/store pipe) -- and the half is a compile-time
+// constant of the place, so the address costs the same two instructions as before.  16-bit counters overflow after
+// 65535 hits, so the block flushes to the global histogram every kHistFlushIters iterations (<= 32768 hits each).
+constexpr int kHistSmemWords  = (kRadixPasses / 2) * kRadixBins * 32;            // 64 KiB
 constexpr size_t kHistSmemBytes = (size_t)kHistSmemWords * 4;
 constexpr int kHistFlushIters = 128;   // 128 iters * (4 keys * 4 loads) * 16 warps = 32768 per lane column
 
-__device__ __forceinline__ void hist_add(uint32_t *col, uint32_t one, int32_t key) {
+// col = the lane's column (sh + lane)
+__device__ __forceinline__ void hist_add(uint32_t *col, int32_t key) {
     const uint32_t k = key_bits(key);
-    atomicAdd(col + (0 * kRadixBins + (k & 255u)) * 16, one);
-    atomicAdd(col + (1 * kRadixBins + ((k >> 8) & 255u)) * 16, one);
-    atomicAdd(col + (2 * kRadixBins + ((k >> 16) & 255u)) * 16, one);
-    atomicAdd(col + (3 * kRadixBins + (k >> 24)) * 16, one);
+#pragma unroll
+    for (int p = 0; p < kRadixPasses; ++p) {
+        const uint32_t d = (k >> (8 * p)) & 255u;
+        atomicAdd(col + ((p >> 1) * kRadixBins + d) * 32, 1u << ((p & 1) * 16));
+    }
 }
 
-// Sum the 32 lane columns of every (place, digit), add into the global histogram, clear.
+// Sum the 32 lane columns of every (place, digit), add into the global histogram, clear.  Thread = one word row
+// = one digit of two places.
 __device__ __forceinline__ void hist_flush(uint32_t *sh, RadixControl *ctl, uint32_t tid) {
+    static_assert(kHistThreads == (kRadixPasses / 2) * kRadixBins, "one thread per word row");
     __syncthreads();
-    for (uint32_t i = tid; i < kRadixPasses * kRadixBins; i += kHistThreads) {
-        uint32_t sum = 0;
+    uint32_t lo = 0, hi = 0;
 #pragma unroll
-        for (uint32_t w = 0; w < 16; ++w) {
-            const uint32_t idx = i * 16 + ((w + (i >> 1)) & 15);   // rotate: conflict-free across threads
-            const uint32_t v = sh[idx];
-            sh[idx] = 0;
-            sum += (v & 0xffffu) + (v >> 16);
-        }
-        if (sum) atomicAdd(&ctl->hist[i >> kRadixBits][i & (kRadixBins - 1)], sum);
+    for (uint32_t l = 0; l < 32; ++l) {
+        const uint32_t idx = tid * 32 + ((l + tid) & 31);        // rotate: conflict-free across threads
+        const uint32_t v = sh[idx];
+        sh[idx] = 0;
+        lo += v & 0xffffu;
+        hi += v >> 16;
     }
+    const uint32_t pp = tid >> kRadixBits, d = tid & (kRadixBins - 1);
+    if (lo) atomicAdd(&ctl->hist[2 * pp][d], lo);
+    if (hi) atomicAdd(&ctl->hist[2 * pp + 1][d], hi);
     __syncthreads();
 }
 
@@ -150,8 +155,7 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
     }
     __syncthreads();
 
-    uint32_t *col = sh + ((tid & 31) >> 1);
-    const uint32_t one = 1u << (16 * (tid & 1));
+    uint32_t *col = sh + (tid & 31);
 
     // Scalar head up to 16-byte alignment, 128-bit body, scalar tail.
     size_t head = ((16 - (reinterpret_cast<uintptr_t>(keys) & 15)) & 15) / 4;
@@ -181,15 +185,15 @@ radix_histogram_kernel(const int32_t *__restrict__ keys, size_t n, RadixControl 
 #pragma unroll
         for (int u = 0; u < kHistUnroll; ++u) {
             if (ok[u]) {
-                hist_add(col, one, r[u].x); hist_add(col, one, r[u].y);
-                hist_add(col, one, r[u].z); hist_add(col, one, r[u].w);
+                hist_add(col, r[u].x); hist_add(col, r[u].y);
+                hist_add(col, r[u].z); hist_add(col, r[u].w);
             }
         }
         if (++iters == kHistFlushIters) { hist_flush(sh, ctl, tid); iters = 0; }
     }
     if (blockIdx.x == 0) {   // < 8 keys in total: cannot overflow anything
-        for (size_t i = tid; i < head; i += kHistThreads) hist_add(col, one, keys[i]);
-        for (size_t i = tail_start + tid; i < n; i += kHistThreads) hist_add(col, one, keys[i]);
+        for (size_t i = tid; i < head; i += kHistThreads) hist_add(col, keys[i]);
+        for (size_t i = tail_start + tid; i < n; i += kHistThreads) hist_add(col, keys[i]);
     }
     hist_flush(sh, ctl, tid);
 

@@ -31,12 +31,12 @@ namespace b200sort {
 // tile's COUNTS only and are laid out when the tile is published, off the look-back's critical path.
 constexpr int kT3StageWords = kT2Tile + kRadixBins * 7 + 64;
 constexpr int kT3Group = 4;                                     // shared-memory atomics a thread issues back to back
-constexpr int kT3Win1 = 12;                                     // nearest earlier tile rows of the group ...
+constexpr int kT3Win1 = 10;                                     // nearest earlier tile rows of the group ...
 constexpr int kT3Win2 = 7;                                      // ... and nearest group rows that fit beside the tile
 constexpr size_t kT3SmemBytes =
     (size_t)kT3StageWords * 4
     + (size_t)2 * kT2Rows * kRadixBins * 4       // digit counters -> positions, this tile's and the previous tile's
-    + (size_t)6 * kRadixBins * 4                 // run {start | length, destination} x2; tile counts | slot; in-group prefix
+    + (size_t)8 * kRadixBins * 4                 // x2: run {start | length, destination}; tile counts | slot; in-group prefix
     + (size_t)(kT3Win1 + kT3Win2) * kRadixBins * 4
     + 256;
 static_assert(kT3SmemBytes <= 115712, "two CTAs per SM");
@@ -66,7 +66,7 @@ __device__ __forceinline__ uint32_t sum_window(const uint32_t (&w)[ROWS], uint32
     return acc;
 }
 
-template <int TIMING, int DEVN = 0>
+template <int TIMING, int DEVN = 0, int INSTEP = 0>
 __device__ __forceinline__ void
 radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n, int pass,
                          RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next, int follow_plan)
@@ -80,10 +80,10 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
     uint32_t *s_table  = reinterpret_cast<uint32_t *>(s_stage + kT3StageWords);          // [2][kRows][256]
     uint2    *s_rg     = reinterpret_cast<uint2 *>(s_table + 2 * kRows * kRadixBins);    // [2][256] {first staged word | keys to
                                                                  //           write << 16, first destination word} of the run
-    uint32_t *s_ptot   = reinterpret_cast<uint32_t *>(s_rg + 2 * kRadixBins);            // [256] the published tile's digit count
+    uint32_t *s_ptot   = reinterpret_cast<uint32_t *>(s_rg + 2 * kRadixBins);            // [2][256] the published tile's digit count
                                                                  //           | its slot's first word << 16
-    uint32_t *s_pin    = s_ptot + kRadixBins;                    // [256] in-group prefix, if the tile summed its group
-    uint32_t *s_win1   = s_pin + kRadixBins;                     // [kT3Win1][256] tile rows before the published tile
+    uint32_t *s_pin    = s_ptot + 2 * kRadixBins;                // [2][256] in-group prefix, if the tile summed its group
+    uint32_t *s_win1   = s_pin + 2 * kRadixBins;                     // [kT3Win1][256] tile rows before the published tile
     uint32_t *s_win2   = s_win1 + kT3Win1 * kRadixBins;          // [kT3Win2][256] group rows before its group
     uint32_t *s_misc   = s_win2 + kT3Win2 * kRadixBins;          // [0..7] warp sums, [8] ticket, [10] tmem base, [16..17] mbarrier,
                                                                  // [20] key count, [21] tile count
@@ -276,19 +276,7 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
         uint32_t *tab_prev = s_table + (cb ^ 1) * kRows * kRadixBins;
         const uint32_t dbg_tile = have_cur ? tile : prev_tile;
         B200_STAMP(0);
-        if (in_a) {
-            // ---- 1: count my keys of `tile` -----------------------------------------------------------------
-            if (have_cur) count_and_park(tile, cb, tab_cur);
-            B200_STAMP(1);
-            bulk_wait_read_all();                                // my bulk copy of the tile before has READ the staging area
-            bar_sync(11, kT2Threads);                            // L: the previous tile's positions are final
-            B200_STAMP(2);
-            // ---- 2: stage my keys of the previous tile ------------------------------------------------------
-            if (have_prev) stage_own(cb, tab_prev);
-            B200_STAMP(3);
-            bar_sync(12, kT2Threads);                            // X: `tile`'s counts are final
-            B200_STAMP(4);
-            // ---- 3: publish `tile` ----------------------------------------------------------------------------
+        auto publish = [&]() {
             uint32_t total = 0;
             if (have_cur) {
                 // thread = digit: `tile`'s count of my digit -> its status row (and, for the last tile of a group,
@@ -321,7 +309,7 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
                     if (r > 0) st_relaxed_gpu(row, kFlagIncl | (p_in + total));
                     uint32_t *grow = status_cur + (tiles_f() + group) * kRadixBins + tid;
                     st_relaxed_gpu(grow, (group == 0 ? kFlagIncl : kFlagLocal) | (p_in + total));
-                    s_pin[tid] = p_in;
+                    s_pin[(INSTEP ? cb : 0u) * kRadixBins + tid] = p_in;
                 }
                 __syncwarp();                                    // the group walk diverges per digit
             }
@@ -357,16 +345,15 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
                 uint32_t add = 0;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) add += (w < (int)warp) ? ms[w] : 0u;
-                s_ptot[tid] = total | ((x - slot + add) << 16);
+                s_ptot[(INSTEP ? cb : 0u) * kRadixBins + tid] = total | ((x - slot + add) << 16);
             }
-            B200_STAMP(5);
-        } else {
-            // ---- 1: the previous tile's prefix and where its runs are staged ----------------------------------
+        };
+        auto resolve = [&]() {
             if (have_prev) {
                 // thread = digit; the rows the look-back needs were published most of an iteration ago and the nearest
                 // of them fetched into shared memory since the last barrier
                 const uint32_t pb = cb ^ 1;
-                const uint32_t pw = s_ptot[bd];
+                const uint32_t pw = s_ptot[(INSTEP ? pb : 0u) * kRadixBins + bd];
                 const uint32_t p_total = pw & 0xffffu;
                 const uint32_t group = prev_tile / kLookGroup, r = prev_tile % kLookGroup;
                 const bool last_tile = (size_t)prev_tile + 1 == tiles_f();
@@ -381,7 +368,7 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
                 load_window<kT3Win1>(s_win1 + bd, have1, w1);
                 load_window<kT3Win2>(s_win2 + bd, have2, w2);
                 uint32_t inprev;
-                if (last_of_group) inprev = s_pin[bd];           // summed when the tile was published
+                if (last_of_group) inprev = s_pin[(INSTEP ? pb : 0u) * kRadixBins + bd];          // summed when the tile was published
                 else               inprev = (r > 0) ? sum_window<kT3Win1, 8>(w1, have1, row - kRadixBins, r) : 0u;
                 const uint32_t gprev = (group > 0) ? sum_window<kT3Win2, 8>(w2, have2, grow - kRadixBins, group) : 0u;
                 B200_STAMP(10);                                  // previous tile resolved
@@ -402,6 +389,65 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
                 else if (r > 0)    st_relaxed_gpu(row, kFlagIncl | (inprev + p_total));
                 __syncwarp();                                    // the walks diverge per digit
             }
+        };
+        auto request_rows = [&](uint32_t p) {                    // one thread: the TMA unit fetches tile p's look-back rows
+            uint32_t have1, have2;
+            window_rows(p, have1, have2);
+            if (have1 + have2 > 0) {
+                const uint32_t group = p / kLookGroup;
+                fence_proxy_async_smem();                        // the reads of the windows' last contents are done (barriers)
+                mbar_expect_tx(mbar, (have1 + have2) * kRadixBins * 4);
+                if (have1) bulk_load(smem_u32(s_win1), status_cur + ((size_t)p - have1) * kRadixBins, have1 * kRadixBins * 4, mbar);
+                if (have2) bulk_load(smem_u32(s_win2), status_cur + (tiles_f() + group - have2) * kRadixBins, have2 * kRadixBins * 4, mbar);
+            }
+        };
+        if (INSTEP) {
+            // ---- R: everybody counts its keys of `tile` ---------------------------------------------------------
+            if (have_cur) count_and_park(tile, cb, tab_cur);
+            B200_STAMP(1);
+            if (in_a) {
+                bulk_wait_read_all();                            // my bulk copy of the tile before has READ the staging area
+                bar_arrive(13, kT2Threads);                      // group A is done with the staging area
+                bar_sync(12, kT2Threads);                        // X: `tile`'s counts are final
+                B200_STAMP(2);
+                publish();                                       // ---- P
+                B200_STAMP(3);
+                bar_sync(11, kT2Threads);                        // L: the previous tile's positions are final
+                B200_STAMP(4);
+            } else {
+                bar_arrive(12, kT2Threads);                      // X: group A may publish
+                // the look-back rows are requested as late as possible: a row fetched before it was published costs a
+                // global round trip of its own (requested during W instead: 0.613 -> 0.646 ms per pass)
+                if (tid == kRadixBins && have_prev) request_rows(prev_tile);
+                B200_STAMP(2);
+                resolve();                                       // ---- D
+                B200_STAMP(3);
+                __threadfence_block();
+                bar_arrive(11, kT2Threads);                      // L: group A may stage
+                bar_sync(1, kRadixBins);                         // ... and so may group B, once ...
+                bar_sync(13, kT2Threads);                        // ... group A's copies have read the staging area
+                B200_STAMP(4);
+            }
+            if (have_prev) stage_own(cb, tab_prev);              // ---- S
+            B200_STAMP(5);
+        } else if (in_a) {
+            // ---- 1: count my keys of `tile` -----------------------------------------------------------------
+            if (have_cur) count_and_park(tile, cb, tab_cur);
+            B200_STAMP(1);
+            bulk_wait_read_all();                                // my bulk copy of the tile before has READ the staging area
+            bar_sync(11, kT2Threads);                            // L: the previous tile's positions are final
+            B200_STAMP(2);
+            // ---- 2: stage my keys of the previous tile ------------------------------------------------------
+            if (have_prev) stage_own(cb, tab_prev);
+            B200_STAMP(3);
+            bar_sync(12, kT2Threads);                            // X: `tile`'s counts are final
+            B200_STAMP(4);
+            // ---- 3: publish `tile` ----------------------------------------------------------------------------
+            publish();
+            B200_STAMP(5);
+        } else {
+            // ---- 1: the previous tile's prefix and where its runs are staged ----------------------------------
+            resolve();
             B200_STAMP(1);
             __threadfence_block();
             bar_arrive(11, kT2Threads);                          // L: group A may stage
@@ -444,17 +490,7 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
             for (int j = 0; j < 3; ++j)
                 if ((uint32_t)j < cnt) st_stream(out_al + g + first + j, e[j]);
         }
-        if (tid == kRadixBins && have_cur) {
-            uint32_t have1, have2;
-            window_rows(tile, have1, have2);
-            if (have1 + have2 > 0) {
-                const uint32_t group = tile / kLookGroup;
-                fence_proxy_async_smem();                        // this iteration's reads of the windows are done (L, X, Y)
-                mbar_expect_tx(mbar, (have1 + have2) * kRadixBins * 4);
-                if (have1) bulk_load(smem_u32(s_win1), status_cur + ((size_t)tile - have1) * kRadixBins, have1 * kRadixBins * 4, mbar);
-                if (have2) bulk_load(smem_u32(s_win2), status_cur + (tiles_f() + group - have2) * kRadixBins, have2 * kRadixBins * 4, mbar);
-            }
-        }
+        if (!INSTEP && tid == kRadixBins && have_cur) request_rows(tile);
         B200_STAMP(7);                                           // previous tile written (bulk copies in flight)
         if (TIMING && g_phase_dbg != nullptr && lane == 0 && (warp == 0 || warp == 8))
             g_phase_dbg[((size_t)dbg_tile * 2 + (warp >> 3)) * 16 + 9] = dbg_tile;
@@ -468,12 +504,12 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(kT2TmemCols) : "memory");
 }
 
-template <int TIMING, int DEVN = 0>
+template <int TIMING, int DEVN = 0, int INSTEP = 0>
 __global__ void __launch_bounds__(kT2Threads, 2)
 radix_onesweep_tma3_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n, int pass,
                            RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next, int follow_plan)
 {
-    radix_onesweep_tma3_body<TIMING, DEVN>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur, status_next, follow_plan);
+    radix_onesweep_tma3_body<TIMING, DEVN, INSTEP>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur, status_next, follow_plan);
 }
 
 }  // namespace b200sort
