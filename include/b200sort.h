@@ -77,8 +77,9 @@ int         b200sort_device_check(void);
  * Any n in [0, B200SORT_MAX_N]; the lab's n (power of two, multiple of 32) is the tested case,
  * ragged n is handled. */
 size_t b200sort_workspace_bytes(size_t n, int algo);
-/* b200sort_radix_i32: the default pass kernel ranks keys with ONE shared-memory atomicAdd per key, which is a
- * stable rank only if the GPU resolves same-address lanes of one warp instruction in lane order.  B200 does
+/* b200sort_radix_i32: the pass kernels rank keys with shared-memory atomicAdds (one per key, or a counting one and a
+ * positioning one), whose return value is a stable rank only if the GPU resolves same-address lanes of one warp
+ * instruction in lane order.  B200 does
  * (tools/atomic_order_probe.cu), PTX does not promise it.  GUARD: a self-test that reproduces the kernels'
  * exact access pattern runs once per DEVICE -- in b200sort_device_check(), or lazily (blocking) in the first
  * sort on that device -- and on failure, or with B200SORT_RANK_SAFE=1 in the environment, every radix entry
