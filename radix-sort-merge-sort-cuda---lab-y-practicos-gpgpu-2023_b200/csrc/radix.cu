@@ -92,12 +92,13 @@ struct Variant {
 
 const Variant kVariants[] = {
     // ---- the shipped shapes ------------------------------------------------------------------------------------
-    { "tma3_16w_2x16_kRankAdd_tmem_keys_bulk_store_staggered", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes,
-      radix_onesweep_tma3_kernel<0>, radix_onesweep_tma3_kernel<0, 1> },   //  0: DEFAULT: persistent CTAs, 16384-key
-                                               //     tiles, keys parked in tensor memory, positions from a second shared
-                                               //     atomic, write-out by TMA bulk copies, the halves of the CTA out of
-                                               //     step, the next tiles prefetched into L2 by the TMA unit.  As the default
-                                               //     CONFIGURATION (radix_sort_impl) arrays below 2^24 keys run shape 1.
+    { "tma3_16w_2x16_kRankAdd_tmem_keys_bulk_store_a_counts_b_resolves", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes,
+      radix_onesweep_tma3_kernel<0, 0, 0, 1>, radix_onesweep_tma3_kernel<0, 1, 0, 1> },   //  0: DEFAULT: persistent CTAs,
+                                               //     16384-key tiles, keys parked in tensor memory, positions from a second
+                                               //     shared atomic, write-out by TMA bulk copies, one half of the CTA counts
+                                               //     and publishes while the other writes out and resolves, the next tiles
+                                               //     prefetched into L2 by the TMA unit.  As the default CONFIGURATION
+                                               //     (radix_sort_impl) arrays below 2^23 keys run shape 1.
     { "pipelined2_16w_ipt20_kRankAdd_pack1_late_ticket", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1>::kTile,
       Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1>,
       radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 0, 0, 1> },   //  1: the ALTERNATE: 10240-key tiles,
@@ -107,14 +108,17 @@ const Variant kVariants[] = {
       Pipelined2Shape<20, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 1>,
       radix_onesweep_pipelined2_kernel<20, 0, 0, 1, 2, 0, 0, 1, 1, 0, 1> },   //  2: the documented-
                                                //     behaviour fallback: shape 1 ranked by ballots
-    { "tma3_16w_2x16_kRankAdd_tmem_keys_bulk_store_staggered_any_size", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes,
-      radix_onesweep_tma3_kernel<0>, radix_onesweep_tma3_kernel<0, 1> },   //  3: shape 0 whatever the size
+    { "tma3_16w_2x16_kRankAdd_tmem_keys_bulk_store_a_counts_b_resolves_any_size", kRankAdd, 0, 1, kT2Threads, kT2Tile,
+      kT3SmemBytes, radix_onesweep_tma3_kernel<0, 0, 0, 1>, radix_onesweep_tma3_kernel<0, 1, 0, 1> },   //  3: shape 0
+                                               //     whatever the size
 #ifdef B200SORT_EXPERIMENTS
     // ---- every other shape measured in rounds 1-2 (profiles/r0*_onesweep_variants.md): make EXPERIMENTS=1 ----------
     // (the phase-timing twins, the earlier TMA kernels, round 1's default and round 1's fallback come first)
     { "TIMING_tma3_16w_2x16", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes, radix_onesweep_tma3_kernel<1> },
     { "tma3_16w_2x16_kRankAdd_in_step", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes, radix_onesweep_tma3_kernel<0, 0, 1> },
     { "TIMING_tma3i_16w_2x16", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes, radix_onesweep_tma3_kernel<1, 0, 1> },
+    { "tma3_16w_2x16_kRankAdd_out_of_step", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes, radix_onesweep_tma3_kernel<0> },
+    { "TIMING_tma3a_16w_2x16", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT3SmemBytes, radix_onesweep_tma3_kernel<1, 0, 0, 1> },
     { "tma_16w_ipt20_kRankAdd_tmem_parked_bulk_store", kRankAdd, 0, 1, kTmaThreads, kTmaTile, kTmaSmemBytes,
       radix_onesweep_tma_kernel<0> },          //     keys + ranks parked in tensor memory, late co-aligned staging, TMA write-out
     { "tma2_16w_2x16_kRankAdd_tmem_keys_second_atomic_bulk_store", kRankAdd, 0, 1, kT2Threads, kT2Tile, kT2SmemBytes,

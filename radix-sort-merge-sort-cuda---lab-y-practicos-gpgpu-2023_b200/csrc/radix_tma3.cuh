@@ -1,26 +1,32 @@
-// radix_tma3.cuh -- k2: one onesweep pass, 16384-key tiles, the two thread groups out of step (included by radix.cu).
+// radix_tma3.cuh -- k2: one onesweep pass, 16384-key tiles, the two halves of the CTA on different jobs (included by
+// radix.cu).
 //
 // Replaces the lab's radix stage (SRM/lab.cu:47-87 radix_sort_kernel + :11-41 exlusiveScan) like the other pass
 // kernels.  Same data path as radix_tma2.cuh (keys parked in tensor memory, positions from a second shared-memory
 // atomicAdd, write-out by TMA bulk copies), another schedule.  There every warp walks R -> D -> S -> W in step, and
-// during D -- the previous tile's look-back sums and staging layout: dependent shared-memory reads and shuffles that
-// only half the CTA works on -- the load/store pipe idles.  Here the halves of the CTA run out of step, so that the
-// pipe-heavy phases (R, S) of one overlap the latency-bound phases (D, P) of the other (t = the tile counted in this
-// iteration, p = the tile counted an iteration ago):
+// during D -- the previous tile's look-back sums and staging layout: dependent shared-memory reads that only half the
+// CTA works on -- the load/store pipe idles.  Here the halves do different things at the same time, so that the
+// pipe-heavy counting of one overlaps the latency-bound write-out and look-back of the other (t = the tile counted in
+// this iteration, p = the tile counted an iteration ago).  The shipped schedule (ACOUNT):
 //
 //            group A (warps 0..7)                         group B (warps 8..15)
-//      1     R  count + park its keys of tile t           D  prefix of tile p (its look-back rows were fetched by TMA);
-//                                                            the first staged word of every run is added to p's counters
-//   -- L --  (B arrives, A waits: p's positions are final) --------------------------------------------------------
-//      2     S  stage its keys of p                       R  count + park its keys of t
-//   -- X --  (everybody: t's counts are final) --------------------------------------------------------------------
-//      3     P  publish t, draw the next ticket, turn     S  stage its keys of p
-//               t's counters into positions inside the
-//               runs, lay out t's staging slots
-//   -- Y --  (everybody: p is staged) -------------------------------------------------------------------------------
-//      4     W  request batch 0 of the next tile;         request batch 0 of the next tile; thread = digit: the tail
-//               thread = digit: bulk copy of p's run      words of p's run; request t's look-back rows
-//               interior, its head words
+//      W     request batch 0 of the next tile             thread = digit: bulk copy of every run of p (16-byte aligned
+//                                                          interior) + its <= 3 + 3 edge words; request t's look-back rows
+//      R|D   count + park its keys of tile t AND those    D  prefix of tile p from the fetched rows; the first staged
+//            of warp w + 8 (same tensor-memory lanes)        word of every run is added to p's counters
+//      P     publish t, draw the next ticket, prefetch
+//            the tile half a round ahead into L2, turn
+//            t's counters into positions inside the
+//            runs, lay out t's staging slots
+//   -- L --  (B arrives, A waits: p's positions are final; nobody still reads the staging area) ------------------
+//      S     stage its keys of p                          stage its keys of p (parked by warp w - 8)
+//   -- Y --  (everybody: p is staged, the ticket is drawn) ------------------------------------------------------
+//
+// A tile is published ~9 k cycles after the barrier Y that precedes its counting and resolved ~17 k cycles later, so
+// its predecessors -- ticketed a few hundred cycles before it -- are in when the look-back reads their rows.  Two
+// earlier schedules are kept as template flags for `make experiments`: every half counts its own keys, out of step
+// (ACOUNT = 0, INSTEP = 0: the tile is published at the END of the iteration and resolved ~5 k cycles later, so the
+// look-back waits for stragglers: 0.606 ms against 0.580) and the same in step (INSTEP: 0.613 ms).
 #pragma once
 #include "radix_tma2.cuh"
 
@@ -66,7 +72,7 @@ __device__ __forceinline__ uint32_t sum_window(const uint32_t (&w)[ROWS], uint32
     return acc;
 }
 
-template <int TIMING, int DEVN = 0, int INSTEP = 0>
+template <int TIMING, int DEVN = 0, int INSTEP = 0, int ACOUNT = 0>
 __device__ __forceinline__ void
 radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n, int pass,
                          RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next, int follow_plan)
@@ -111,7 +117,6 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
     const bool in_a = tid < kRadixBins;                          // warps 0..7 : thread = digit
     const uint32_t bd = tid - kRadixBins;                        // warps 8..15: thread - 256 = digit
     const uint32_t sh = (warp & 1) * 16;
-    const uint32_t wofs = warp * (32 * kT2Ipt) + lane;           // a warp owns 1024 consecutive keys of the tile
     // word offset of `out` inside its 16-byte chunk: word g of the array is word g + gmis of the aligned base
     const uint32_t gmis = (uint32_t)((reinterpret_cast<uintptr_t>(out) >> 2) & 3u);
     int32_t *out_al = out - gmis;
@@ -147,11 +152,11 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
     const uint32_t tmem_warp = tmem_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * 64u;
 
     int32_t ka[kT2Batch], kb[kT2Batch];                          // batch 0 / batch 1 of the tile being counted
-    auto load_batch = [&](uint32_t t, int batch, int32_t (&k)[kT2Batch]) {
+    auto load_batch_of = [&](uint32_t t, uint32_t wsel, int batch, int32_t (&k)[kT2Batch]) {   // warp wsel's slice
         const size_t tile_base = (size_t)t * kTile;
         const size_t n_now = n_f();
         const uint32_t valid = (n_now - tile_base < (size_t)kTile) ? (uint32_t)(n_now - tile_base) : (uint32_t)kTile;
-        const uint32_t o = wofs + batch * (32 * kT2Batch);
+        const uint32_t o = wsel * (32 * kT2Ipt) + lane + batch * (32 * kT2Batch);
         const int32_t *src = in + tile_base + o;
         if (valid == (uint32_t)kTile) {
 #pragma unroll
@@ -161,6 +166,7 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
             for (int i = 0; i < kT2Batch; ++i) k[i] = (o + i * 32 < valid) ? ld_stream(src + i * 32) : 0x7FFFFFFF;
         }
     };
+    auto load_batch = [&](uint32_t t, int batch, int32_t (&k)[kT2Batch]) { load_batch_of(t, warp, batch, k); };
     // one shared-memory atomicAdd per key on the warp's half of its counter row.  COUNT: the result is not used (rank
     // phase); otherwise it is the key's staged position, and the key goes there.  A hot digit (the histogram kernel
     // found one value holding > 1/8 of the keys, or a quarter of the warp's first keys agree with lane 0's) is handled
@@ -230,6 +236,28 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
         tmem_st16(tmem_warp + cb * 32u, ka);
         sweep(kb, wt, true);
         tmem_st16(tmem_warp + cb * 32u + 16u, kb);
+    };
+    // ACOUNT: group A's warp w counts and parks its own keys AND those of warp w + 8 (same lane quadrant of tensor
+    // memory, the columns of w + 8; the counters of w + 8: row (w >> 1) + 4, the same half), so that the tile can be
+    // published without waiting for group B.  Two register sets, four batches, every load one batch ahead.
+    auto count_and_park_both = [&](uint32_t t, uint32_t cb, uint32_t *tab_cur) {
+        uint32_t *wt = tab_cur + (warp >> 1) * kRadixBins;
+        const uint32_t tm = tmem_warp + cb * 32u;
+        load_batch(t, 1, kb);
+        sweep(ka, wt, true);
+        tmem_st16(tm, ka);
+        tmem_wait_st();                                          // (not needed for the registers; measured: 0.580 ms with
+        load_batch_of(t, warp + 8, 0, ka);                       //  the two waits, 0.590 without -- they pace the warp)
+        sweep(kb, wt, true);
+        tmem_st16(tm + 16u, kb);
+        tmem_wait_st();
+        load_batch_of(t, warp + 8, 1, kb);
+        sweep(ka, wt + 4 * kRadixBins, true);
+        tmem_st16(tm + 128u, ka);
+        sweep(kb, wt + 4 * kRadixBins, true);
+        tmem_st16(tm + 128u + 16u, kb);
+        tmem_wait_st();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // warp w + 8 reads them an iteration from now
     };
     // S: stage the previous tile's keys of this warp: keys come back from tensor memory, positions from the second atomic
     auto stage_own = [&](uint32_t cb, uint32_t *tab_prev) {
@@ -309,7 +337,7 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
                     if (r > 0) st_relaxed_gpu(row, kFlagIncl | (p_in + total));
                     uint32_t *grow = status_cur + (tiles_f() + group) * kRadixBins + tid;
                     st_relaxed_gpu(grow, (group == 0 ? kFlagIncl : kFlagLocal) | (p_in + total));
-                    s_pin[(INSTEP ? cb : 0u) * kRadixBins + tid] = p_in;
+                    s_pin[((INSTEP || ACOUNT) ? cb : 0u) * kRadixBins + tid] = p_in;
                 }
                 __syncwarp();                                    // the group walk diverges per digit
             }
@@ -345,7 +373,7 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
                 uint32_t add = 0;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) add += (w < (int)warp) ? ms[w] : 0u;
-                s_ptot[(INSTEP ? cb : 0u) * kRadixBins + tid] = total | ((x - slot + add) << 16);
+                s_ptot[((INSTEP || ACOUNT) ? cb : 0u) * kRadixBins + tid] = total | ((x - slot + add) << 16);
             }
         };
         auto resolve = [&]() {
@@ -353,7 +381,7 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
                 // thread = digit; the rows the look-back needs were published most of an iteration ago and the nearest
                 // of them fetched into shared memory since the last barrier
                 const uint32_t pb = cb ^ 1;
-                const uint32_t pw = s_ptot[(INSTEP ? pb : 0u) * kRadixBins + bd];
+                const uint32_t pw = s_ptot[((INSTEP || ACOUNT) ? pb : 0u) * kRadixBins + bd];
                 const uint32_t p_total = pw & 0xffffu;
                 const uint32_t group = prev_tile / kLookGroup, r = prev_tile % kLookGroup;
                 const bool last_tile = (size_t)prev_tile + 1 == tiles_f();
@@ -368,7 +396,7 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
                 load_window<kT3Win1>(s_win1 + bd, have1, w1);
                 load_window<kT3Win2>(s_win2 + bd, have2, w2);
                 uint32_t inprev;
-                if (last_of_group) inprev = s_pin[(INSTEP ? pb : 0u) * kRadixBins + bd];          // summed when the tile was published
+                if (last_of_group) inprev = s_pin[((INSTEP || ACOUNT) ? pb : 0u) * kRadixBins + bd];          // summed when the tile was published
                 else               inprev = (r > 0) ? sum_window<kT3Win1, 8>(w1, have1, row - kRadixBins, r) : 0u;
                 const uint32_t gprev = (group > 0) ? sum_window<kT3Win2, 8>(w2, have2, grow - kRadixBins, group) : 0u;
                 B200_STAMP(10);                                  // previous tile resolved
@@ -401,7 +429,30 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
                 if (have2) bulk_load(smem_u32(s_win2), status_cur + (tiles_f() + group - have2) * kRadixBins, have2 * kRadixBins * 4, mbar);
             }
         };
-        if (INSTEP) {
+        if (ACOUNT) {
+            if (in_a) {
+                // ---- R: count my keys of `tile` and my partner warp's; P: publish it ---------------------------
+                if (have_cur) count_and_park_both(tile, cb, tab_cur);
+                B200_STAMP(1);
+                bar_sync(2, kRadixBins);                         // group A: `tile`'s counts are final
+                publish();
+                B200_STAMP(2);
+                bar_sync(11, kT2Threads);                        // L: the previous tile's positions are final
+                B200_STAMP(3);
+            } else {
+                // ---- D: the previous tile's prefix and where its runs are staged ------------------------------
+                resolve();
+                B200_STAMP(1);
+                bulk_wait_read_all();                            // my bulk copy of the tile before has READ the staging area
+                __threadfence_block();
+                bar_arrive(11, kT2Threads);                      // L: group A may stage
+                bar_sync(1, kRadixBins);                         // ... and so may group B
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");   // my keys were parked by warp - 8
+                B200_STAMP(3);
+            }
+            if (have_prev) stage_own(cb, tab_prev);              // ---- S
+            B200_STAMP(5);
+        } else if (INSTEP) {
             // ---- R: everybody counts its keys of `tile` ---------------------------------------------------------
             if (have_cur) count_and_park(tile, cb, tab_cur);
             B200_STAMP(1);
@@ -467,30 +518,63 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
         // for the 16-byte aligned interior, the <= 3 + 3 edge words by ordinary stores; group B asks for the look-back
         // rows of `tile` and goes on to resolve it ----------------------------------------------------------------
         const uint32_t next = s_misc[8];
-        if (next < tiles_f()) load_batch(next, 0, ka);
-        if (have_prev) {
-            // thread = digit in both groups: A sends the interior and the head, B the tail
-            const uint2 rg = s_rg[(cb ^ 1) * kRadixBins + (in_a ? tid : bd)];
-            const uint32_t start = rg.x & 0xffffu, c = rg.x >> 16, g = rg.y;
-            uint32_t head = (4u - (g & 3u)) & 3u;
-            if (head > c) head = c;
-            const uint32_t body = (c - head) & ~3u;
+        if (ACOUNT) {
+            // group A only loads (it counts for everybody); group B, thread = digit, writes the previous tile: one bulk
+            // copy for the run's 16-byte aligned interior, the <= 3 + 3 edge words by ordinary stores
             if (in_a) {
-                B200_CHECK_AT(13, body == 0 || (((g + head) & 3u) == 0 && ((start + head) & 3u) == 0));
-                B200_CHECK_AT(14, (size_t)g - gmis + c <= n_f() && start + c <= (uint32_t)kT3StageWords);
-                if (body > 0) bulk_store(out_al + g + head, stage_s + (start + head) * 4u, body * 4u);
-                bulk_commit();
+                if (next < tiles_f()) load_batch(next, 0, ka);
+            } else {
+                if (have_prev) {
+                    const uint2 rg = s_rg[(cb ^ 1) * kRadixBins + bd];
+                    const uint32_t start = rg.x & 0xffffu, c = rg.x >> 16, g = rg.y;
+                    uint32_t head = (4u - (g & 3u)) & 3u;
+                    if (head > c) head = c;
+                    const uint32_t body = (c - head) & ~3u;
+                    const uint32_t tail = c - head - body;
+                    B200_CHECK_AT(13, body == 0 || (((g + head) & 3u) == 0 && ((start + head) & 3u) == 0));
+                    B200_CHECK_AT(14, (size_t)g - gmis + c <= n_f() && start + c <= (uint32_t)kT3StageWords);
+                    if (body > 0) bulk_store(out_al + g + head, stage_s + (start + head) * 4u, body * 4u);
+                    bulk_commit();
+                    int32_t e[6];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        e[j]     = ((uint32_t)j < head) ? s_stage[start + j] : 0;
+                        e[3 + j] = ((uint32_t)j < tail) ? s_stage[start + head + body + j] : 0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        if ((uint32_t)j < head) st_stream(out_al + g + j, e[j]);
+                        if ((uint32_t)j < tail) st_stream(out_al + g + head + body + j, e[3 + j]);
+                    }
+                }
+                if (tid == kRadixBins && have_cur) request_rows(tile);
             }
-            const uint32_t cnt = in_a ? head : c - head - body;  // my edge: words [first, first + cnt) of the run
-            const uint32_t first = in_a ? 0u : head + body;
-            int32_t e[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) e[j] = ((uint32_t)j < cnt) ? s_stage[start + first + j] : 0;
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                if ((uint32_t)j < cnt) st_stream(out_al + g + first + j, e[j]);
+        } else {
+            if (next < tiles_f()) load_batch(next, 0, ka);
+            if (have_prev) {
+                // thread = digit in both groups: A sends the interior and the head, B the tail
+                const uint2 rg = s_rg[(cb ^ 1) * kRadixBins + (in_a ? tid : bd)];
+                const uint32_t start = rg.x & 0xffffu, c = rg.x >> 16, g = rg.y;
+                uint32_t head = (4u - (g & 3u)) & 3u;
+                if (head > c) head = c;
+                const uint32_t body = (c - head) & ~3u;
+                if (in_a) {
+                    B200_CHECK_AT(13, body == 0 || (((g + head) & 3u) == 0 && ((start + head) & 3u) == 0));
+                    B200_CHECK_AT(14, (size_t)g - gmis + c <= n_f() && start + c <= (uint32_t)kT3StageWords);
+                    if (body > 0) bulk_store(out_al + g + head, stage_s + (start + head) * 4u, body * 4u);
+                    bulk_commit();
+                }
+                const uint32_t cnt = in_a ? head : c - head - body;  // my edge: words [first, first + cnt) of the run
+                const uint32_t first = in_a ? 0u : head + body;
+                int32_t e[3];
+    #pragma unroll
+                for (int j = 0; j < 3; ++j) e[j] = ((uint32_t)j < cnt) ? s_stage[start + first + j] : 0;
+    #pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if ((uint32_t)j < cnt) st_stream(out_al + g + first + j, e[j]);
+            }
+            if (!INSTEP && tid == kRadixBins && have_cur) request_rows(tile);
         }
-        if (!INSTEP && tid == kRadixBins && have_cur) request_rows(tile);
         B200_STAMP(7);                                           // previous tile written (bulk copies in flight)
         if (TIMING && g_phase_dbg != nullptr && lane == 0 && (warp == 0 || warp == 8))
             g_phase_dbg[((size_t)dbg_tile * 2 + (warp >> 3)) * 16 + 9] = dbg_tile;
@@ -504,12 +588,12 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(kT2TmemCols) : "memory");
 }
 
-template <int TIMING, int DEVN = 0, int INSTEP = 0>
+template <int TIMING, int DEVN = 0, int INSTEP = 0, int ACOUNT = 0>
 __global__ void __launch_bounds__(kT2Threads, 2)
 radix_onesweep_tma3_kernel(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_buf, size_t n, int pass,
                            RadixControl *ctl, uint32_t *status_cur, uint32_t *status_next, int follow_plan)
 {
-    radix_onesweep_tma3_body<TIMING, DEVN, INSTEP>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur, status_next, follow_plan);
+    radix_onesweep_tma3_body<TIMING, DEVN, INSTEP, ACOUNT>(in_buf, out_buf, tmp_buf, n, pass, ctl, status_cur, status_next, follow_plan);
 }
 
 }  // namespace b200sort

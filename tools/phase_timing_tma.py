@@ -30,6 +30,20 @@ mid = d[tiles // 8: tiles * 7 // 8]
 mid = mid[(mid[:, 0, 7] > 0) & (mid[:, 1, 7] > 0) & (mid[:, 1, 10] > 0)]
 if b"tma3" in want:
     # the staggered schedule: the two groups name their phases differently
+    if b"tma3a" in want:
+        na = ["start", "A counted all", "A published", "L passed", "-", "A staged", "Y passed", "loads issued"]
+        nb = ["start", "B resolved", "-", "barriers passed", "-", "B staged", "Y passed", "written"]
+        for grp, label, nm, idx in ((0, "group A (warp 0)", na, (0, 1, 2, 3, 5, 6, 7)), (1, "group B (warp 8)", nb, (0, 1, 3, 5, 6, 7))):
+            print(label)
+            for a, b2 in zip(idx[:-1], idx[1:]):
+                dt = mid[:, grp, b2] - mid[:, grp, a]
+                print(f"  {nm[a]:>18s} -> {nm[b2]:<18s} mean {dt.mean():8.0f} cyc   p50 {np.median(dt):8.0f}   p90 {np.percentile(dt, 90):8.0f}")
+            tot = mid[:, grp, 7] - mid[:, grp, 0]
+            print(f"  iteration mean {tot.mean():.0f} cyc ({tot.mean()/1.965e3:.2f} us)")
+        for a, b2, label in ((0, 11, "start -> fetched rows landed (mbarrier)"), (11, 10, "look-back sums"), (10, 1, "start words added to the counters")):
+            dt = mid[:, 1, b2] - mid[:, 1, a]
+            print(f"group B: {label:<48s} mean {dt.mean():8.0f} cyc   p50 {np.median(dt):8.0f}   p90 {np.percentile(dt, 90):8.0f}   max {dt.max():8.0f}")
+        sys.exit(0)
     if b"tma3i" in want:
         na = ["start", "A counted", "X passed", "A published", "L passed", "A staged", "Y passed", "written"]
         nb = ["start", "B counted", "rows requested", "B resolved", "barriers passed", "B staged", "Y passed", "tails written"]
