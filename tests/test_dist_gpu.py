@@ -97,13 +97,24 @@ def test_device_planner_equals_host_planner(world, bits):
     assert err == 1
 
 
+@pytest.mark.parametrize("shape", [0, 3])                  # 3: the large-array pass kernel whatever the size
 @pytest.mark.parametrize("world", [2, 8])
 @pytest.mark.parametrize("dist_name", ["uniform", "skewed90", "all_equal"])
-def test_sync_free_path_with_simulated_ranks(world, dist_name):
+def test_sync_free_path_with_simulated_ranks(world, dist_name, shape):
     """Device plan -> planned partition (bulk copies) -> local sort with the key count read from the device record:
     the whole multi-GPU sequence on one GPU, every destination compared with np.sort of the keys it owns."""
     import torch
     L = lib()
+    if shape >= L.b200sort_radix_num_variants():
+        pytest.skip("shape not compiled")
+    check(L.b200sort_radix_set_variant(shape))
+    try:
+        _sync_free_path(L, torch, world, dist_name)
+    finally:
+        L.b200sort_radix_set_variant(0)
+
+
+def _sync_free_path(L, torch, world, dist_name):
     bits, n = 14, 300000
     srcs = [datagen.make(dist_name, n + 1000 * r, seed=60 + r) for r in range(world)]
     all_hist = np.stack([b200dist.host_histogram(k, bits) for k in srcs])
