@@ -342,21 +342,10 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
                 __syncwarp();                                    // the group walk diverges per digit
             }
             // The next tile's ticket is drawn right after the publication: from ticket to publication every tile takes
-            // the same write + count + stage time.
-            if (tid == 0) {
-                const uint32_t t_next = atomicAdd(&ctl->ticket[pass], 1u);
-                s_misc[8] = t_next;
-                // ... and the tile some CTA will draw an iteration from now is sent for: with two CTAs of this size an
-                // SM has 28 KB of L1 left, which is all the loads it can have in flight, so how long a load is in
-                // flight (HBM or L2) bounds how fast the keys come in
-                const size_t t_far = (size_t)t_next + gridDim.x / 2;
-                if (t_far < tiles_f()) {
-                    const size_t left = (n_f() - t_far * kTile) * 4;
-                    const uintptr_t a0 = reinterpret_cast<uintptr_t>(in + t_far * kTile) & ~(uintptr_t)15;
-                    const uint32_t bytes = (uint32_t)((left < (size_t)kTile * 4 ? left : (size_t)kTile * 4) & ~(size_t)15);
-                    if (bytes > 0) bulk_prefetch_l2(reinterpret_cast<const void *>(a0), bytes);
-                }
-            }
+            // the same write + count + stage time.  (The atomic is issued here and its result used after the slot scan:
+            // its global round trip would otherwise hold the whole group at the scan's barrier.)
+            uint32_t t_next = 0;
+            if (tid == 0) t_next = atomicAdd(&ctl->ticket[pass], 1u);
             {
                 // the staging slots of `tile`: whole 16-byte chunks + four spare words per digit, in digit order
                 const uint32_t slot = have_cur ? ((total + 3u) & ~3u) + 4u : 0u;
@@ -374,6 +363,19 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
 #pragma unroll
                 for (int w = 0; w < 8; ++w) add += (w < (int)warp) ? ms[w] : 0u;
                 s_ptot[((INSTEP || ACOUNT) ? cb : 0u) * kRadixBins + tid] = total | ((x - slot + add) << 16);
+            }
+            if (tid == 0) {
+                s_misc[8] = t_next;
+                // ... and the tile some CTA will draw half a round of tickets from now is sent for: with two CTAs of
+                // this size an SM has 28 KB of L1 left, which is all the loads it can have in flight, so how long a load
+                // is in flight (HBM or L2) bounds how fast the keys come in
+                const size_t t_far = (size_t)t_next + gridDim.x / 2;
+                if (t_far < tiles_f()) {
+                    const size_t left = (n_f() - t_far * kTile) * 4;
+                    const uintptr_t a0 = reinterpret_cast<uintptr_t>(in + t_far * kTile) & ~(uintptr_t)15;
+                    const uint32_t bytes = (uint32_t)((left < (size_t)kTile * 4 ? left : (size_t)kTile * 4) & ~(size_t)15);
+                    if (bytes > 0) bulk_prefetch_l2(reinterpret_cast<const void *>(a0), bytes);
+                }
             }
         };
         auto resolve = [&]() {
@@ -524,6 +526,9 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
             if (in_a) {
                 if (next < tiles_f()) load_batch(next, 0, ka);
             } else {
+                // t's look-back rows are requested first: they were published ~10 k cycles ago and are consumed after
+                // the write-out, so the fetch costs the look-back nothing
+                if (tid == kRadixBins && have_cur) request_rows(tile);
                 if (have_prev) {
                     const uint2 rg = s_rg[(cb ^ 1) * kRadixBins + bd];
                     const uint32_t start = rg.x & 0xffffu, c = rg.x >> 16, g = rg.y;
@@ -533,21 +538,20 @@ radix_onesweep_tma3_body(const int32_t *in_buf, int32_t *out_buf, int32_t *tmp_b
                     const uint32_t tail = c - head - body;
                     B200_CHECK_AT(13, body == 0 || (((g + head) & 3u) == 0 && ((start + head) & 3u) == 0));
                     B200_CHECK_AT(14, (size_t)g - gmis + c <= n_f() && start + c <= (uint32_t)kT3StageWords);
-                    if (body > 0) bulk_store(out_al + g + head, stage_s + (start + head) * 4u, body * 4u);
-                    bulk_commit();
-                    int32_t e[6];
+                    int32_t e[6];        // the edge words are read before the copy is issued (~14 instructions per lane), stored after
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         e[j]     = ((uint32_t)j < head) ? s_stage[start + j] : 0;
                         e[3 + j] = ((uint32_t)j < tail) ? s_stage[start + head + body + j] : 0;
                     }
+                    if (body > 0) bulk_store(out_al + g + head, stage_s + (start + head) * 4u, body * 4u);
+                    bulk_commit();
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         if ((uint32_t)j < head) st_stream(out_al + g + j, e[j]);
                         if ((uint32_t)j < tail) st_stream(out_al + g + head + body + j, e[3 + j]);
                     }
                 }
-                if (tid == kRadixBins && have_cur) request_rows(tile);
             }
         } else {
             if (next < tiles_f()) load_batch(next, 0, ka);
