@@ -6,11 +6,14 @@
 //   k1  radix_histogram_kernel (radix_hist.cuh)   ONE read of the keys (128-bit loads) builds all four
 //        digit histograms; its last block turns them into exclusive bases, decides which passes are
 //        skippable, flags hot digits, plans the buffers and zeroes the first status buffer.   4 B/key
-//   k2  one pass, 8 B/key, in three compiled families (b200sort_radix_set_variant picks a shape):
-//        radix_onesweep_pipelined2_kernel (radix_pipelined.cuh)  DEFAULT: persistent CTAs, every warp
-//              a worker, one shared-memory atomicAdd per key as the rank (16-bit counters, two warps
-//              per row), delayed two-level decoupled look-back, double-buffered staging,
-//              coalesced scatter;
+//   k2  one pass, 8 B/key, in several compiled families (b200sort_radix_set_variant picks a shape):
+//        radix_onesweep_tma3_kernel (radix_tma3.cuh)  DEFAULT from 2^23 keys on: persistent CTAs, 16384-key
+//              tiles, keys parked in tensor memory, positions from a second shared-memory atomicAdd,
+//              write-out by TMA bulk copies, tiles prefetched into L2 by the TMA unit;
+//        radix_onesweep_pipelined2_kernel (radix_pipelined.cuh)  the default below 2^23 keys: persistent
+//              CTAs, every warp a worker, one shared-memory atomicAdd per key as the rank (16-bit
+//              counters, two warps per row), delayed two-level decoupled look-back, double-buffered
+//              staging, coalesced scatter by the load/store pipe;
 //        radix_onesweep_kernel (radix_tile.cuh)  one tile per CTA; rank by MATCH / ballots /
 //              atomicOr table / atomicAdd; one- or two-level look-back; optional clusters;
 //        radix_onesweep_pipelined_kernel (radix_pipelined.cuh)  14 worker warps + 2 chain warps.
