@@ -142,14 +142,11 @@ const Variant kVariants[] = {
                                                //     previous tile's look-back rows fetched by bulk load under the ranking
     { "TIMING_pipelined2_prefetch", kRankAdd, 0, 1, 512, Pipelined2Shape<20, 1, 0, 1>::kTile,
       Pipelined2Shape<20, 1, 0, 1>::kSmemBytes, radix_onesweep_pipelined2_kernel<20, 1, 0, 1, 2, 0, 0, 1, 0, 1> },   //  8
-    B200_PP2X_VARIANT(20, 0, 1),               //  0: DEFAULT (fastest measured, 0.712 ms/pass): persistent CTAs,
-                                               //     10240-key tiles, delayed two-level look-back, 16-bit counters
-                                               //     (two warps per row)
+    // ---- round 1's table (its default, B200_PP2X_VARIANT(20, 0, 1), and its fallback are listed above) ----
     B200_VARIANT(16, 18, 2, kRankAdd, 1),      //  1: 9216
     B200_VARIANT(16, 16, 2, kRankAdd, 1),      //  2: 8192
     B200_VARIANT(8, 24, 3, kRankAdd, 1),       //  3: 6144, 256 threads
     B200_VARIANT(8, 16, 4, kRankAdd, 1),       //  4: 4096, 4 CTAs/SM
-    B200_VARIANT(16, 16, 2, kRankBallot, 1),   //  5: the documented-behaviour fallback
     B200_VARIANT(16, 16, 2, kRankAtomic, 1),   //  6
     B200_VARIANT(16, 16, 2, kRankMatch, 1),    //  7
     B200_VARIANT(8, 24, 3, kRankBallot, 1),    //  8

@@ -58,8 +58,13 @@ def test_status_strings_and_validation_without_a_gpu():
     L = b200sort.lib()
     assert L.b200sort_version().startswith(b"b200sort")
     assert L.b200sort_status_string(0) == b"ok"
-    assert L.b200sort_radix_num_variants() >= 1
-    assert L.b200sort_radix_set_variant(-1) == 1 and L.b200sort_radix_set_variant(0) == 0
+    nv = L.b200sort_radix_num_variants()
+    assert nv >= 4                                   # default, small-array shape, ballot fallback, default at any size
+    names = [L.b200sort_radix_variant_name(v) for v in range(nv)]
+    assert all(names) and len(set(names)) == nv and L.b200sort_radix_variant_name(nv) is None
+    assert b"kRankBallot" in names[2]                # the documented-behaviour fallback keeps its index
+    assert L.b200sort_radix_set_variant(-1) == 1 and L.b200sort_radix_set_variant(nv) == 1
+    assert L.b200sort_radix_set_variant(0) == 0
     assert L.b200sort_radix_tile() >= 2048 and L.b200sort_block_sort_tile() >= 1024
     # argument validation happens before any device work
     assert L.b200sort_radix_i32(None, None, 10, None, 0, None) == 1            # NULL keys
